@@ -1,0 +1,164 @@
+/*
+ * ohs.h — C ABI of the B200-native Open Headstage DSP engine (libohs_cuda.so).
+ *
+ * This is the drop-in boundary for ONE path of KiloHertzian/Open-Headstage: the DSP core that
+ * `Plugin::process` runs per host buffer (reference src/lib.rs:1156-1211):
+ *
+ *     10-band parametric EQ  ->  4-path binaural partitioned convolution  ->  output gain
+ *     (src/dsp/parametric_eq.rs)   (src/dsp/convolution.rs)                   (src/lib.rs:1202-1207)
+ *
+ * re-posed as a batched renderer: one engine handle owns `n_streams` independent stereo chains (each the
+ * equivalent of one reference `ConvolutionEngine` + one `StereoParametricEQ`), resident in HBM, processed
+ * together by hand-written sm_100a kernels.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Every entry point cites the reference interface it replaces.  The Rust-side binding a maintainer of the
+ * reference would add (extern "C" block, wrapper structs with the reference's method names, build.rs
+ * additions) is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 (OHS_OK) or a negative ohs_status; ohs_last_error() gives the message of the
+ *     last failure on the calling thread.  Nothing throws or aborts across the boundary (the reference
+ *     panics on bad EQ parameters, src/dsp/parametric_eq.rs:111; here that is OHS_ERR_INVALID).
+ *   - audio is planar f32: in/out[(stream*2 + channel) * row_stride + frame], channel 0 = left, 1 = right
+ *     (reference: `let [left, right] = buffer.as_slice()`, src/lib.rs:1175).
+ *   - one handle = one CUDA stream; a handle is not re-entrant (the reference API is `&mut self`); distinct
+ *     handles are independent.
+ *   - there is no CPU fallback: if no CUDA device is usable, ohs_create fails.
+ */
+#ifndef OHS_H
+#define OHS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OHS_ABI_VERSION 1
+
+typedef enum ohs_status {
+    OHS_OK = 0,
+    OHS_ERR_INVALID = -1,     /* bad argument (null handle, index out of range, unsupported block size, ...) */
+    OHS_ERR_CUDA = -2,        /* a CUDA runtime call failed; message holds cudaGetErrorString */
+    OHS_ERR_NO_DEVICE = -3,   /* no usable CUDA device (no CPU fallback exists) */
+    OHS_ERR_NYQUIST = -4,     /* EQ design: 2*fc > fs  (biquad Errors::OutsideNyquist) */
+    OHS_ERR_NEGATIVE_Q = -5,  /* EQ design: q < 0      (biquad Errors::NegativeQ) */
+    OHS_ERR_ALIGNMENT = -6    /* device/host audio pointer or row stride not 16-byte aligned */
+} ohs_status;
+
+/* src/dsp/convolution.rs:26-33  enum ConvolutionPath { Lsl, Lsr, Rsl, Rsr }
+ * (L/R speaker -> l/r ear; out_l = Lsl + Rsl, out_r = Lsr + Rsr, :229-230) */
+typedef enum ohs_path { OHS_PATH_LSL = 0, OHS_PATH_LSR = 1, OHS_PATH_RSL = 2, OHS_PATH_RSR = 3 } ohs_path;
+
+/* src/dsp/parametric_eq.rs:25-35  enum FilterType (declaration order) */
+typedef enum ohs_filter_type {
+    OHS_FILTER_PEAK = 0, OHS_FILTER_LOWSHELF = 1, OHS_FILTER_HIGHSHELF = 2, OHS_FILTER_LOWPASS = 3,
+    OHS_FILTER_HIGHPASS = 4, OHS_FILTER_BANDPASS = 5, OHS_FILTER_NOTCH = 6, OHS_FILTER_ALLPASS = 7
+} ohs_filter_type;
+
+#define OHS_ALL (-1)        /* "every stream" for the per-stream setters */
+#define OHS_MAX_BANDS 10    /* NUM_EQ_BANDS, src/lib.rs:40 */
+
+/* Replaces the compile-time constants and constructor arguments of the reference:
+ *   BLOCK_SIZE / FFT_SIZE (src/dsp/convolution.rs:22-23), NUM_EQ_BANDS (src/lib.rs:40),
+ *   StereoParametricEQ::new(num_bands, sample_rate) (src/dsp/parametric_eq.rs:132). */
+typedef struct ohs_config {
+    int32_t n_streams;    /* independent stereo chains held by this engine (>= 1) */
+    int32_t block;        /* engine block B in frames: 64, 128, 256, 512 or 1024; FFT size is 2*B */
+    int32_t max_taps;     /* longest impulse response set_ir will be given; sizes the delay line: P = ceil(max_taps/B) */
+    int32_t n_bands;      /* EQ bands per channel, 0..OHS_MAX_BANDS */
+    int32_t n_hrir_sets;  /* distinct 4-path HRIR sets (>= 1); every stream starts bound to set 0 */
+    int32_t n_eq_sets;    /* distinct EQ coefficient sets (>= 1); every stream starts bound to set 0 */
+    int32_t device;       /* CUDA device ordinal */
+    float sample_rate;    /* Hz; used by ohs_eq_update_band */
+} ohs_config;
+
+typedef struct ohs_engine ohs_engine;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------ */
+/* ConvolutionEngine::new (src/dsp/convolution.rs:87-108) + StereoParametricEQ::new (src/dsp/parametric_eq.rs:132-142)
+ * for n_streams chains: every path's IR is silence (one all-zero partition, :44-65), every band is
+ * PeakingEQ(0 dB)@20 Hz Q 0.707 and disabled (:63-76), gain 1, eq_enable 0 (src/lib.rs:433-434), bypass 0. */
+int ohs_create(const ohs_config* cfg, ohs_engine** out);
+int ohs_destroy(ohs_engine* h);
+int ohs_abi_version(void);
+const char* ohs_last_error(void);
+
+/* ---- HRIR set-up ------------------------------------------------------------------------------------------ */
+/* ConvolutionEngine::set_ir(path, &[f32]) (src/dsp/convolution.rs:111-139).  The IR is cut into B-frame chunks,
+ * each zero-padded to 2B and transformed on the GPU; len == 0 gives one silent partition (:114-118).
+ * As in the reference (:135-138) the convolution history of every stream bound to `hrir_set` is cleared.
+ * (Difference, documented in DESIGN.md: the reference clears only the history of the one path; here the delay
+ * line is shared by the four paths, so all four restart.  Identical whenever IRs are set before streaming.) */
+int ohs_set_ir(ohs_engine* h, int hrir_set, int path, const float* ir, size_t len);
+/* ir_fft_partitions.len() of that path, as asserted by the reference test (src/dsp/convolution.rs:395-399). */
+int ohs_num_partitions(ohs_engine* h, int hrir_set, int path, int* out);
+/* Which HRIR set a stream (or OHS_ALL) convolves with; clears that stream's convolution history. */
+int ohs_bind_stream_hrir(ohs_engine* h, int stream, int hrir_set);
+/* Device-resident filter spectra of all sets, for a caller-side NCCL broadcast: pointer and byte
+ * size of the table the render kernel reads.  ohs_commit_filters uploads pending set_ir work first; after an
+ * external overwrite (broadcast receive) call ohs_mark_filters_external so pending host IRs do not overwrite it. */
+int ohs_commit_filters(ohs_engine* h);
+int ohs_filter_table(ohs_engine* h, void** dev_ptr, size_t* bytes);
+int ohs_mark_filters_external(ohs_engine* h, int hrir_set, int partitions);
+
+/* ---- EQ --------------------------------------------------------------------------------------------------- */
+/* biquad 0.4.2 Coefficients::<f32>::from_params as called by BiquadFilter::update_coeffs
+ * (src/dsp/parametric_eq.rs:86-114).  Pure host function; out = {b0, b1, b2, a1, a2} normalised by a0. */
+int ohs_eq_design(int filter_type, float fs, float fc, float q, float gain_db, float out[5]);
+/* StereoParametricEQ::update_band_coeffs(band_idx, sample_rate, &BandConfig) (src/dsp/parametric_eq.rs:144-164):
+ * same coefficients and `enabled` for left and right, filter state kept.  band >= n_bands is ignored (returns OK)
+ * exactly like the reference (:145).  Uses cfg.sample_rate. */
+int ohs_eq_update_band(ohs_engine* h, int eq_set, int band, int filter_type, float fc, float q, float gain_db, int enabled);
+/* Same, with the five coefficients supplied as data. */
+int ohs_eq_set_band(ohs_engine* h, int eq_set, int band, const float coeffs[5], int enabled);
+int ohs_bind_stream_eq(ohs_engine* h, int stream, int eq_set);
+/* StereoParametricEQ::reset_all_bands_state (src/dsp/parametric_eq.rs:181-188; Plugin::reset src/lib.rs:1152-1154). */
+int ohs_eq_reset(ohs_engine* h);
+/* StereoParametricEQ::calculate_frequency_response (src/dsp/parametric_eq.rs:191-209), enabled bands of `eq_set`. */
+int ohs_eq_frequency_response(ohs_engine* h, int eq_set, const float* freqs, float* out, size_t n);
+
+/* ---- chain switches (Plugin::process, src/lib.rs:1169-1207) ------------------------------------------------- */
+int ohs_set_eq_enable(ohs_engine* h, int enable);          /* params.eq_enable (:1179) */
+int ohs_set_conv_enable(ohs_engine* h, int enable);        /* 0 = EQ/gain only: StereoParametricEQ::process_block alone */
+int ohs_set_bypass(ohs_engine* h, int bypass);             /* params.master_bypass (:1169): output = input, state untouched */
+int ohs_set_gain(ohs_engine* h, int stream, float gain);   /* output_gain, one value per call (:1202-1207); stream or OHS_ALL */
+/* Clears convolution history (as a fresh ConvolutionEngine with the same IRs would have). */
+int ohs_conv_reset(ohs_engine* h);
+
+/* ---- processing ------------------------------------------------------------------------------------------- */
+/* The per-block process call: EQ (if enabled) -> convolution -> gain for every stream, n_frames frames each
+ * (ConvolutionEngine::process_block src/dsp/convolution.rs:141 + StereoParametricEQ::process_block
+ * src/dsp/parametric_eq.rs:166 + gain loop src/lib.rs:1202-1207).  n_frames must be a multiple of B: whole engine
+ * blocks, i.e. the zero-latency case of the reference's FIFO (host block = multiple of BLOCK_SIZE).
+ * in == out (in place) is allowed.  row_stride = frames between consecutive (stream, channel) rows (>= n_frames).
+ * Device flavour: pointers are device memory on cfg.device; the call only enqueues on the engine's stream. */
+int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_frames, size_t row_stride);
+/* Host flavour: pointers are host memory (pinned memory from ohs_host_alloc gives full PCIe speed); the call
+ * stages time chunks through HBM with copies overlapped against the kernels and returns when `out` is complete. */
+int ohs_process(ohs_engine* h, const float* in, float* out, size_t n_frames, size_t row_stride);
+/* Arbitrary host-block length for ONE-call-per-host-buffer use: the reference's input/output FIFO adaptation
+ * (src/dsp/convolution.rs:141-182) including the zero-filled output while fewer than n frames are ready. */
+int ohs_process_fifo(ohs_engine* h, const float* in, float* out, size_t n_frames, size_t row_stride);
+int ohs_sync(ohs_engine* h);
+/* The engine's cudaStream_t (as void*) so callers can order their own work / NCCL calls against it. */
+int ohs_cuda_stream(ohs_engine* h, void** stream);
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches evidence). */
+int ohs_launch_count(ohs_engine* h, uint64_t* out);
+/* Elapsed device time (ms) of the render kernels of the most recent ohs_process_device call; blocks until done. */
+int ohs_last_kernel_ms(ohs_engine* h, float* ms);
+
+/* pinned host memory helpers */
+int ohs_host_alloc(void** p, size_t bytes);
+int ohs_host_free(void* p);
+
+/* ---- state export / import (chunked offline renders resume bit-exactly) ---------------------- */
+int ohs_state_bytes(ohs_engine* h, size_t* bytes);
+int ohs_state_export(ohs_engine* h, void* host_buf, size_t bytes);
+int ohs_state_import(ohs_engine* h, const void* host_buf, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OHS_H */

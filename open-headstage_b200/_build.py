@@ -1,0 +1,42 @@
+"""In-tree nvcc build of the C-ABI library (libohs_cuda.so) for sm_100a.  nvcc cross-compiles without a GPU."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB = os.path.join(HERE, "libohs_cuda.so")
+SOURCES = [os.path.join(HERE, "csrc", "ohs_api.cu")]
+DEPS = SOURCES + [os.path.join(HERE, "csrc", "ohs_kernels.cuh"), os.path.join(ROOT, "include", "ohs.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+    # no -use_fast_math: denormals are kept (-ftz=false) and division/sqrt stay IEEE, as on the reference's CPU path
+]
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found; libohs_cuda.so cannot be built (there is no CPU fallback)")
+    return p
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if force or is_stale():
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, *SOURCES]
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+        subprocess.check_call(cmd, cwd=ROOT)
+    return LIB

@@ -1,0 +1,838 @@
+// ohs_api.cu — the C ABI of include/ohs.h over the kernels of ohs_kernels.cuh.
+//
+// Host-side state of one engine handle: the per-stream bindings (HRIR set, EQ set, gain), host copies of the
+// impulse responses and EQ coefficients (uploaded lazily, on the next process call, so a burst of set_ir /
+// update_band calls costs one upload — the reference recomputes all 20 biquads on every process() call,
+// src/lib.rs:1180-1193), and the device-resident stream state: frequency-domain delay line, overlap-save block,
+// biquad states.  No CPU fallback exists anywhere in this file: without a CUDA device ohs_create fails.
+#include "../../include/ohs.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ohs_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define OHS_CUDA(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t _e = (expr);                                                                                \
+        if (_e != cudaSuccess) return fail(OHS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                           __FILE__, __LINE__);                                                 \
+    } while (0)
+
+#define OHS_CHECK_HANDLE(h) \
+    do { if (!(h)) return fail(OHS_ERR_INVALID, "null engine handle"); } while (0)
+
+constexpr int kPipe = 3;  // staging buffers of the host-pointer path
+
+}  // namespace
+
+struct ohs_engine {
+    ohs_config cfg{};
+    int B = 0, N = 0, pmax = 1, G = 1;
+    cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    bool timed = false;
+
+    // device
+    int* d_stream_hrir = nullptr;
+    int* d_stream_eq = nullptr;
+    float* d_stream_gain = nullptr;
+    float4* d_filt = nullptr;
+    int* d_set_parts = nullptr;
+    float2* d_fdl = nullptr;
+    float2* d_prev = nullptr;
+    float* d_eqc = nullptr;
+    float4* d_eqs = nullptr;
+    float2* d_tw = nullptr;
+    float* d_ir = nullptr;
+    int* d_set_list = nullptr;
+    unsigned char* d_set_flags = nullptr;
+    size_t filt_bytes = 0;
+
+    // host mirrors
+    std::vector<int> h_stream_hrir, h_stream_eq, h_set_parts, h_path_parts;
+    std::vector<float> h_gain, h_eqc;
+    std::vector<std::vector<float>> h_ir;  // [set*4 + path]
+    std::vector<unsigned char> set_dirty, set_external;
+    bool any_set_dirty = false, eqc_dirty = true, bind_dirty = true, gain_dirty = true;
+
+    int head = 0;
+    int eq_enable = 0, conv_enable = 1, bypass = 0;
+    uint64_t launches = 0;
+
+    // host-pointer path
+    float* d_stage[kPipe] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in[kPipe] = {}, ev_comp[kPipe] = {}, ev_out[kPipe] = {};
+    size_t stage_frames = 0;
+
+    // FIFO adaptor (src/dsp/convolution.rs:141-182)
+    std::vector<float> fifo_in, fifo_out;  // [row][cap]
+    size_t fifo_cap = 0, fifo_in_len = 0, fifo_out_len = 0;
+};
+
+namespace {
+
+using namespace ohs;
+
+template <int N, int G> int launch_render_ng(ohs_engine* h, const RenderParams& p) {
+    using SM = RenderSmem<N, G>;
+    static bool attr_set[64] = {};
+    int dev = h->cfg.device;
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        OHS_CUDA(cudaFuncSetAttribute(render_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kBytes));
+        attr_set[dev] = true;
+    }
+    const int grid = (p.n_streams + G - 1) / G;
+    render_kernel<N, G><<<grid, SM::kThreads, SM::kBytes, h->stream>>>(p);
+    OHS_CUDA(cudaGetLastError());
+    h->launches++;
+    return OHS_OK;
+}
+
+template <int N> int launch_render_n(ohs_engine* h, const RenderParams& p) {
+    switch (h->G) {
+        case 1: return launch_render_ng<N, 1>(h, p);
+        case 2: if constexpr (RenderSmem<N, 2>::kBytes <= 227 * 1024) return launch_render_ng<N, 2>(h, p); break;
+        case 3: if constexpr (RenderSmem<N, 3>::kBytes <= 227 * 1024) return launch_render_ng<N, 3>(h, p); break;
+    }
+    return fail(OHS_ERR_INVALID, "unsupported streams-per-CTA %d for block %d", h->G, N / 2);
+}
+
+int launch_render(ohs_engine* h, const RenderParams& p) {
+    switch (h->N) {
+        case 128: return launch_render_n<128>(h, p);
+        case 256: return launch_render_n<256>(h, p);
+        case 512: return launch_render_n<512>(h, p);
+        case 1024: return launch_render_n<1024>(h, p);
+        case 2048: return launch_render_n<2048>(h, p);
+    }
+    return fail(OHS_ERR_INVALID, "unsupported block size %d", h->B);
+}
+
+size_t render_smem_bytes(int N, int G) {
+#define OHS_CASE(n)                                                     \
+    case n:                                                             \
+        return G == 1 ? RenderSmem<n, 1>::kBytes : G == 2 ? RenderSmem<n, 2>::kBytes : RenderSmem<n, 3>::kBytes;
+    switch (N) { OHS_CASE(128) OHS_CASE(256) OHS_CASE(512) OHS_CASE(1024) OHS_CASE(2048) }
+#undef OHS_CASE
+    return ~(size_t)0;
+}
+
+template <int N> int launch_setup_n(ohs_engine* h, int max_parts, int n_sets) {
+    using SM = SetupSmem<N>;
+    static bool attr_set[64] = {};
+    int dev = h->cfg.device;
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        OHS_CUDA(cudaFuncSetAttribute(setup_filters_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kBytes));
+        attr_set[dev] = true;
+    }
+    dim3 grid(max_parts, n_sets);
+    setup_filters_kernel<N><<<grid, SM::T, SM::kBytes, h->stream>>>(h->d_ir, h->d_filt, h->d_tw, h->d_set_list, h->d_set_parts, h->pmax);
+    OHS_CUDA(cudaGetLastError());
+    h->launches++;
+    return OHS_OK;
+}
+
+int launch_setup(ohs_engine* h, int max_parts, int n_sets) {
+    switch (h->N) {
+        case 128: return launch_setup_n<128>(h, max_parts, n_sets);
+        case 256: return launch_setup_n<256>(h, max_parts, n_sets);
+        case 512: return launch_setup_n<512>(h, max_parts, n_sets);
+        case 1024: return launch_setup_n<1024>(h, max_parts, n_sets);
+        case 2048: return launch_setup_n<2048>(h, max_parts, n_sets);
+    }
+    return fail(OHS_ERR_INVALID, "unsupported block size %d", h->B);
+}
+
+int clear_history(ohs_engine* h, bool only_flagged) {
+    clear_history_kernel<<<h->cfg.n_streams, 256, 0, h->stream>>>(h->d_fdl, h->d_prev, h->d_stream_hrir, h->cfg.n_streams,
+                                                                 only_flagged ? h->d_set_flags : nullptr,
+                                                                 (size_t)h->pmax * h->N, (size_t)h->B);
+    OHS_CUDA(cudaGetLastError());
+    h->launches++;
+    return OHS_OK;
+}
+
+int upload_bindings(ohs_engine* h) {
+    if (h->bind_dirty) {
+        OHS_CUDA(cudaMemcpyAsync(h->d_stream_hrir, h->h_stream_hrir.data(), sizeof(int) * h->cfg.n_streams, cudaMemcpyHostToDevice, h->stream));
+        OHS_CUDA(cudaMemcpyAsync(h->d_stream_eq, h->h_stream_eq.data(), sizeof(int) * h->cfg.n_streams, cudaMemcpyHostToDevice, h->stream));
+        h->bind_dirty = false;
+    }
+    if (h->gain_dirty) {
+        OHS_CUDA(cudaMemcpyAsync(h->d_stream_gain, h->h_gain.data(), sizeof(float) * h->cfg.n_streams, cudaMemcpyHostToDevice, h->stream));
+        h->gain_dirty = false;
+    }
+    if (h->eqc_dirty) {
+        OHS_CUDA(cudaMemcpyAsync(h->d_eqc, h->h_eqc.data(), sizeof(float) * h->h_eqc.size(), cudaMemcpyHostToDevice, h->stream));
+        h->eqc_dirty = false;
+    }
+    // pageable host sources: the async copies above are staged by the runtime before returning
+    return OHS_OK;
+}
+
+int commit_filters(ohs_engine* h) {
+    int rc = upload_bindings(h);
+    if (rc) return rc;
+    if (!h->any_set_dirty) return OHS_OK;
+    const int n_sets = h->cfg.n_hrir_sets;
+    const size_t per_path = (size_t)h->pmax * h->B;
+    std::vector<int> list;
+    std::vector<float> padded(4 * per_path);
+    int max_parts = 1;
+    for (int s = 0; s < n_sets; ++s) {
+        if (!h->set_dirty[s]) continue;
+        std::fill(padded.begin(), padded.end(), 0.f);
+        int parts = 1;
+        for (int p = 0; p < 4; ++p) {
+            const std::vector<float>& ir = h->h_ir[(size_t)s * 4 + p];
+            std::copy(ir.begin(), ir.end(), padded.begin() + p * per_path);
+            parts = std::max(parts, h->h_path_parts[(size_t)s * 4 + p]);
+        }
+        h->h_set_parts[s] = parts;
+        max_parts = std::max(max_parts, parts);
+        OHS_CUDA(cudaMemcpyAsync(h->d_ir + (size_t)s * 4 * per_path, padded.data(), sizeof(float) * padded.size(), cudaMemcpyHostToDevice, h->stream));
+        OHS_CUDA(cudaStreamSynchronize(h->stream));  // `padded` is reused
+        list.push_back(s);
+    }
+    OHS_CUDA(cudaMemcpyAsync(h->d_set_parts, h->h_set_parts.data(), sizeof(int) * n_sets, cudaMemcpyHostToDevice, h->stream));
+    OHS_CUDA(cudaMemcpyAsync(h->d_set_list, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, h->stream));
+    OHS_CUDA(cudaMemcpyAsync(h->d_set_flags, h->set_dirty.data(), n_sets, cudaMemcpyHostToDevice, h->stream));
+    OHS_CUDA(cudaStreamSynchronize(h->stream));
+    rc = launch_setup(h, max_parts, (int)list.size());
+    if (rc) return rc;
+    // set_ir clears the history of the streams that use the set (src/dsp/convolution.rs:135-138)
+    rc = clear_history(h, true);
+    if (rc) return rc;
+    std::fill(h->set_dirty.begin(), h->set_dirty.end(), 0);
+    h->any_set_dirty = false;
+    return OHS_OK;
+}
+
+// biquad 0.4.2 Coefficients::<f32>::from_params, f32 arithmetic and libm like the crate (src/dsp/parametric_eq.rs:105-111)
+int eq_design_impl(int type, float fs, float fc, float q, float gain_db, float out[5]) {
+    if (2.0f * fc > fs) return fail(OHS_ERR_NYQUIST, "EQ design: 2*fc (%g) > fs (%g)", 2.0 * fc, (double)fs);
+    if (q < 0.0f) return fail(OHS_ERR_NEGATIVE_Q, "EQ design: negative Q %g", (double)q);
+    const float pi = 3.14159265358979323846f;
+    const float omega = 2.0f * pi * fc / fs;
+    const float sn = sinf(omega), cs = cosf(omega);
+    const float alpha = sn / (2.0f * q);
+    float b0, b1, b2, a0, a1, a2;
+    bool divide = false;
+    if (type == OHS_FILTER_PEAK || type == OHS_FILTER_LOWSHELF || type == OHS_FILTER_HIGHSHELF) {
+        const float a = powf(10.0f, gain_db / 40.0f);
+        divide = true;
+        if (type == OHS_FILTER_PEAK) {
+            b0 = 1.0f + alpha * a; b1 = -2.0f * cs; b2 = 1.0f - alpha * a;
+            a0 = 1.0f + alpha / a; a1 = -2.0f * cs; a2 = 1.0f - alpha / a;
+        } else {
+            const float beta = 2.0f * alpha * sqrtf(a);
+            const float ap = a + 1.0f, am = a - 1.0f;
+            if (type == OHS_FILTER_LOWSHELF) {
+                b0 = a * (ap - am * cs + beta); b1 = 2.0f * a * (am - ap * cs); b2 = a * (ap - am * cs - beta);
+                a0 = ap + am * cs + beta; a1 = -2.0f * (am + ap * cs); a2 = ap + am * cs - beta;
+            } else {
+                b0 = a * (ap + am * cs + beta); b1 = -2.0f * a * (am + ap * cs); b2 = a * (ap + am * cs - beta);
+                a0 = ap - am * cs + beta; a1 = 2.0f * (am - ap * cs); a2 = ap - am * cs - beta;
+            }
+        }
+    } else {
+        a0 = 1.0f + alpha; a1 = -2.0f * cs; a2 = 1.0f - alpha;
+        switch (type) {
+            case OHS_FILTER_LOWPASS: b0 = (1.0f - cs) * 0.5f; b1 = 1.0f - cs; b2 = (1.0f - cs) * 0.5f; break;
+            case OHS_FILTER_HIGHPASS: b0 = (1.0f + cs) * 0.5f; b1 = -(1.0f + cs); b2 = (1.0f + cs) * 0.5f; break;
+            case OHS_FILTER_BANDPASS: b0 = sn / 2.0f; b1 = 0.0f; b2 = -(sn / 2.0f); break;
+            case OHS_FILTER_NOTCH: b0 = 1.0f; b1 = -2.0f * cs; b2 = 1.0f; break;
+            case OHS_FILTER_ALLPASS: b0 = 1.0f - alpha; b1 = -2.0f * cs; b2 = 1.0f + alpha; break;
+            default: return fail(OHS_ERR_INVALID, "unknown filter type %d", type);
+        }
+    }
+    if (divide) {
+        out[0] = b0 / a0; out[1] = b1 / a0; out[2] = b2 / a0; out[3] = a1 / a0; out[4] = a2 / a0;
+    } else {
+        const float inv = 1.0f / a0;
+        out[0] = b0 * inv; out[1] = b1 * inv; out[2] = b2 * inv; out[3] = a1 * inv; out[4] = a2 * inv;
+    }
+    return OHS_OK;
+}
+
+int set_band_host(ohs_engine* h, int eq_set, int band, const float c[5], int enabled) {
+    if (eq_set < 0 || eq_set >= h->cfg.n_eq_sets) return fail(OHS_ERR_INVALID, "eq_set %d out of range", eq_set);
+    if (band < 0 || band >= h->cfg.n_bands) return OHS_OK;  // silently ignored, src/dsp/parametric_eq.rs:145
+    float* dst = h->h_eqc.data() + ((size_t)eq_set * kMaxBands + band) * kEqCoefStride;
+    for (int i = 0; i < 5; ++i) dst[i] = c[i];
+    dst[5] = enabled ? 1.0f : 0.0f;
+    h->eqc_dirty = true;
+    return OHS_OK;
+}
+
+int check_audio_args(ohs_engine* h, const void* in, const void* out, size_t n_frames, size_t row_stride, bool device) {
+    if (!in || !out) return fail(OHS_ERR_INVALID, "null audio pointer");
+    if (h->conv_enable && n_frames % (size_t)h->B) return fail(OHS_ERR_INVALID, "n_frames %zu is not a multiple of the engine block %d (use ohs_process_fifo)", n_frames, h->B);
+    if (row_stride < n_frames) return fail(OHS_ERR_INVALID, "row_stride %zu < n_frames %zu", row_stride, n_frames);
+    if (device && (((uintptr_t)in | (uintptr_t)out) & 15u || (row_stride & 3u)))
+        return fail(OHS_ERR_ALIGNMENT, "device audio pointers must be 16-byte aligned and row_stride a multiple of 4 frames");
+    return OHS_OK;
+}
+
+int pick_streams_per_cta(const ohs_engine* h) {
+    if (const char* e = getenv("OHS_STREAMS_PER_CTA")) {
+        const int g = atoi(e);
+        if (g >= 1 && g <= kMaxG && render_smem_bytes(h->N, g) <= 227 * 1024) return g;
+    }
+    cudaDeviceProp prop{};
+    int sms = 148;
+    if (cudaGetDeviceProperties(&prop, h->cfg.device) == cudaSuccess) sms = prop.multiProcessorCount;
+    // fill the EQ warp (3 x 10 lanes) when that still leaves at least one CTA per SM
+    for (int g = kMaxG; g >= 1; --g) {
+        if (render_smem_bytes(h->N, g) > 227 * 1024) continue;
+        if (g == 1 || (h->cfg.n_streams + g - 1) / g >= sms) return g;
+    }
+    return 1;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ohs_abi_version(void) { return OHS_ABI_VERSION; }
+const char* ohs_last_error(void) { return g_last_error.c_str(); }
+
+int ohs_eq_design(int filter_type, float fs, float fc, float q, float gain_db, float out[5]) {
+    if (!out) return fail(OHS_ERR_INVALID, "null output");
+    return eq_design_impl(filter_type, fs, fc, q, gain_db, out);
+}
+
+int ohs_create(const ohs_config* cfg, ohs_engine** out) {
+    if (!cfg || !out) return fail(OHS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const int B = cfg->block;
+    if (!(B == 64 || B == 128 || B == 256 || B == 512 || B == 1024)) return fail(OHS_ERR_INVALID, "block must be 64, 128, 256, 512 or 1024 (got %d)", B);
+    if (cfg->n_streams < 1) return fail(OHS_ERR_INVALID, "n_streams must be >= 1");
+    if (cfg->n_bands < 0 || cfg->n_bands > OHS_MAX_BANDS) return fail(OHS_ERR_INVALID, "n_bands must be 0..%d", OHS_MAX_BANDS);
+    if (cfg->n_hrir_sets < 1 || cfg->n_eq_sets < 1) return fail(OHS_ERR_INVALID, "need at least one HRIR set and one EQ set");
+    if (cfg->max_taps < 1) return fail(OHS_ERR_INVALID, "max_taps must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(OHS_ERR_NO_DEVICE, "no CUDA device available; this engine has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(OHS_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+    OHS_CUDA(cudaSetDevice(cfg->device));
+
+    ohs_engine* h = new ohs_engine();
+    h->cfg = *cfg;
+    h->B = B;
+    h->N = 2 * B;
+    h->pmax = (cfg->max_taps + B - 1) / B;
+    h->G = pick_streams_per_cta(h);
+    const int S = cfg->n_streams;
+    const size_t per_path = (size_t)h->pmax * B;
+
+    h->h_stream_hrir.assign(S, 0);
+    h->h_stream_eq.assign(S, 0);
+    h->h_gain.assign(S, 1.0f);
+    h->h_set_parts.assign(cfg->n_hrir_sets, 1);
+    h->h_path_parts.assign((size_t)cfg->n_hrir_sets * 4, 1);
+    h->h_ir.assign((size_t)cfg->n_hrir_sets * 4, std::vector<float>());
+    h->set_dirty.assign(cfg->n_hrir_sets, 0);
+    h->set_external.assign(cfg->n_hrir_sets, 0);
+    h->h_eqc.assign((size_t)cfg->n_eq_sets * kMaxBands * kEqCoefStride, 0.f);
+    {
+        // BiquadFilter::new: PeakingEQ(0 dB) @ 20 Hz, Q 0.707, disabled (src/dsp/parametric_eq.rs:63-76)
+        float c[5] = {1.f, 0.f, 0.f, 0.f, 0.f};
+        if (2.0f * 20.0f <= cfg->sample_rate) eq_design_impl(OHS_FILTER_PEAK, cfg->sample_rate, 20.0f, 0.707f, 0.0f, c);
+        for (int e = 0; e < cfg->n_eq_sets; ++e)
+            for (int b = 0; b < kMaxBands; ++b) {
+                float* dst = h->h_eqc.data() + ((size_t)e * kMaxBands + b) * kEqCoefStride;
+                for (int i = 0; i < 5; ++i) dst[i] = c[i];
+            }
+    }
+
+#define OHS_TRY(expr)                                   \
+    do {                                                \
+        cudaError_t _e = (expr);                        \
+        if (_e != cudaSuccess) {                        \
+            fail(OHS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+            ohs_destroy(h);                             \
+            return OHS_ERR_CUDA;                        \
+        }                                               \
+    } while (0)
+    OHS_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    OHS_TRY(cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking));
+    OHS_TRY(cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking));
+    OHS_TRY(cudaEventCreate(&h->ev_k0));
+    OHS_TRY(cudaEventCreate(&h->ev_k1));
+    for (int i = 0; i < kPipe; ++i) {
+        OHS_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        OHS_TRY(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+        OHS_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+    h->filt_bytes = sizeof(float4) * (size_t)cfg->n_hrir_sets * h->pmax * h->N;
+    OHS_TRY(cudaMalloc(&h->d_stream_hrir, sizeof(int) * S));
+    OHS_TRY(cudaMalloc(&h->d_stream_eq, sizeof(int) * S));
+    OHS_TRY(cudaMalloc(&h->d_stream_gain, sizeof(float) * S));
+    OHS_TRY(cudaMalloc(&h->d_filt, h->filt_bytes));
+    OHS_TRY(cudaMalloc(&h->d_set_parts, sizeof(int) * cfg->n_hrir_sets));
+    OHS_TRY(cudaMalloc(&h->d_set_list, sizeof(int) * cfg->n_hrir_sets));
+    OHS_TRY(cudaMalloc(&h->d_set_flags, cfg->n_hrir_sets));
+    OHS_TRY(cudaMalloc(&h->d_fdl, sizeof(float2) * (size_t)S * h->pmax * h->N));
+    OHS_TRY(cudaMalloc(&h->d_prev, sizeof(float2) * (size_t)S * B));
+    OHS_TRY(cudaMalloc(&h->d_eqc, sizeof(float) * h->h_eqc.size()));
+    OHS_TRY(cudaMalloc(&h->d_eqs, sizeof(float4) * (size_t)S * kMaxBands));
+    OHS_TRY(cudaMalloc(&h->d_tw, sizeof(float2) * h->N));
+    OHS_TRY(cudaMalloc(&h->d_ir, sizeof(float) * (size_t)cfg->n_hrir_sets * 4 * per_path));
+    OHS_TRY(cudaMemsetAsync(h->d_filt, 0, h->filt_bytes, h->stream));  // default IR = silence (src/dsp/convolution.rs:44-65)
+    OHS_TRY(cudaMemsetAsync(h->d_fdl, 0, sizeof(float2) * (size_t)S * h->pmax * h->N, h->stream));
+    OHS_TRY(cudaMemsetAsync(h->d_prev, 0, sizeof(float2) * (size_t)S * B, h->stream));
+    OHS_TRY(cudaMemsetAsync(h->d_eqs, 0, sizeof(float4) * (size_t)S * kMaxBands, h->stream));
+    OHS_TRY(cudaMemsetAsync(h->d_ir, 0, sizeof(float) * (size_t)cfg->n_hrir_sets * 4 * per_path, h->stream));
+    {
+        std::vector<float2> tw(h->N);
+        for (int m = 0; m < h->N; ++m) {
+            const double a = -2.0 * 3.14159265358979323846 * (double)m / (double)h->N;
+            tw[m] = make_float2((float)cos(a), (float)sin(a));
+        }
+        OHS_TRY(cudaMemcpyAsync(h->d_tw, tw.data(), sizeof(float2) * h->N, cudaMemcpyHostToDevice, h->stream));
+        OHS_TRY(cudaMemcpyAsync(h->d_set_parts, h->h_set_parts.data(), sizeof(int) * cfg->n_hrir_sets, cudaMemcpyHostToDevice, h->stream));
+        OHS_TRY(cudaStreamSynchronize(h->stream));
+    }
+#undef OHS_TRY
+    *out = h;
+    return OHS_OK;
+}
+
+int ohs_destroy(ohs_engine* h) {
+    if (!h) return OHS_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {h->d_stream_hrir, h->d_stream_eq, h->d_stream_gain, h->d_filt, h->d_set_parts, h->d_set_list, h->d_set_flags,
+                    h->d_fdl, h->d_prev, h->d_eqc, h->d_eqs, h->d_tw, h->d_ir, h->d_stage[0], h->d_stage[1], h->d_stage[2]};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < kPipe; ++i) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->ev_k0) cudaEventDestroy(h->ev_k0);
+    if (h->ev_k1) cudaEventDestroy(h->ev_k1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->h2d) cudaStreamDestroy(h->h2d);
+    if (h->d2h) cudaStreamDestroy(h->d2h);
+    delete h;
+    return OHS_OK;
+}
+
+// ---- HRIR ---------------------------------------------------------------------------------------------------
+int ohs_set_ir(ohs_engine* h, int hrir_set, int path, const float* ir, size_t len) {
+    OHS_CHECK_HANDLE(h);
+    if (hrir_set < 0 || hrir_set >= h->cfg.n_hrir_sets) return fail(OHS_ERR_INVALID, "hrir_set %d out of range", hrir_set);
+    if (path < 0 || path > 3) return fail(OHS_ERR_INVALID, "path %d out of range", path);
+    if (len > 0 && !ir) return fail(OHS_ERR_INVALID, "null impulse response");
+    if (len > (size_t)h->pmax * h->B) return fail(OHS_ERR_INVALID, "impulse response of %zu taps exceeds max_taps capacity %d", len, h->pmax * h->B);
+    std::vector<float>& dst = h->h_ir[(size_t)hrir_set * 4 + path];
+    dst.assign(ir, ir + len);
+    // ir.chunks(BLOCK_SIZE).count(), or one silent partition for an empty slice (src/dsp/convolution.rs:114-132)
+    h->h_path_parts[(size_t)hrir_set * 4 + path] = len == 0 ? 1 : (int)((len + h->B - 1) / h->B);
+    h->set_dirty[hrir_set] = 1;
+    h->set_external[hrir_set] = 0;
+    h->any_set_dirty = true;
+    return OHS_OK;
+}
+
+int ohs_num_partitions(ohs_engine* h, int hrir_set, int path, int* out) {
+    OHS_CHECK_HANDLE(h);
+    if (!out || hrir_set < 0 || hrir_set >= h->cfg.n_hrir_sets || path < 0 || path > 3) return fail(OHS_ERR_INVALID, "bad argument");
+    *out = h->h_path_parts[(size_t)hrir_set * 4 + path];
+    return OHS_OK;
+}
+
+int ohs_bind_stream_hrir(ohs_engine* h, int stream, int hrir_set) {
+    OHS_CHECK_HANDLE(h);
+    if (hrir_set < 0 || hrir_set >= h->cfg.n_hrir_sets) return fail(OHS_ERR_INVALID, "hrir_set %d out of range", hrir_set);
+    if (stream != OHS_ALL && (stream < 0 || stream >= h->cfg.n_streams)) return fail(OHS_ERR_INVALID, "stream %d out of range", stream);
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    if (stream == OHS_ALL) std::fill(h->h_stream_hrir.begin(), h->h_stream_hrir.end(), hrir_set);
+    else h->h_stream_hrir[stream] = hrir_set;
+    h->bind_dirty = true;
+    // a re-bound stream starts from empty history, like a ConvolutionEngine that was just given its IRs
+    if (stream == OHS_ALL) {
+        int rc = upload_bindings(h);
+        if (rc) return rc;
+        return clear_history(h, false);
+    }
+    OHS_CUDA(cudaMemsetAsync(h->d_fdl + (size_t)stream * h->pmax * h->N, 0, sizeof(float2) * (size_t)h->pmax * h->N, h->stream));
+    OHS_CUDA(cudaMemsetAsync(h->d_prev + (size_t)stream * h->B, 0, sizeof(float2) * (size_t)h->B, h->stream));
+    return OHS_OK;
+}
+
+int ohs_commit_filters(ohs_engine* h) {
+    OHS_CHECK_HANDLE(h);
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    return commit_filters(h);
+}
+
+int ohs_filter_table(ohs_engine* h, void** dev_ptr, size_t* bytes) {
+    OHS_CHECK_HANDLE(h);
+    if (!dev_ptr || !bytes) return fail(OHS_ERR_INVALID, "null output");
+    *dev_ptr = h->d_filt;
+    *bytes = h->filt_bytes;
+    return OHS_OK;
+}
+
+int ohs_mark_filters_external(ohs_engine* h, int hrir_set, int partitions) {
+    OHS_CHECK_HANDLE(h);
+    if (hrir_set < 0 || hrir_set >= h->cfg.n_hrir_sets) return fail(OHS_ERR_INVALID, "hrir_set %d out of range", hrir_set);
+    if (partitions < 1 || partitions > h->pmax) return fail(OHS_ERR_INVALID, "partitions %d out of range 1..%d", partitions, h->pmax);
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    h->set_dirty[hrir_set] = 0;
+    h->set_external[hrir_set] = 1;
+    h->h_set_parts[hrir_set] = partitions;
+    for (int p = 0; p < 4; ++p) h->h_path_parts[(size_t)hrir_set * 4 + p] = partitions;
+    h->any_set_dirty = false;
+    for (unsigned char d : h->set_dirty) h->any_set_dirty |= d != 0;
+    OHS_CUDA(cudaMemcpyAsync(h->d_set_parts, h->h_set_parts.data(), sizeof(int) * h->cfg.n_hrir_sets, cudaMemcpyHostToDevice, h->stream));
+    OHS_CUDA(cudaStreamSynchronize(h->stream));
+    return OHS_OK;
+}
+
+// ---- EQ -----------------------------------------------------------------------------------------------------
+int ohs_eq_update_band(ohs_engine* h, int eq_set, int band, int filter_type, float fc, float q, float gain_db, int enabled) {
+    OHS_CHECK_HANDLE(h);
+    if (band < 0 || band >= h->cfg.n_bands) {
+        if (eq_set < 0 || eq_set >= h->cfg.n_eq_sets) return fail(OHS_ERR_INVALID, "eq_set %d out of range", eq_set);
+        return OHS_OK;
+    }
+    float c[5];
+    int rc = eq_design_impl(filter_type, h->cfg.sample_rate, fc, q, gain_db, c);
+    if (rc) return rc;
+    return set_band_host(h, eq_set, band, c, enabled);
+}
+
+int ohs_eq_set_band(ohs_engine* h, int eq_set, int band, const float coeffs[5], int enabled) {
+    OHS_CHECK_HANDLE(h);
+    if (!coeffs) return fail(OHS_ERR_INVALID, "null coefficients");
+    return set_band_host(h, eq_set, band, coeffs, enabled);
+}
+
+int ohs_bind_stream_eq(ohs_engine* h, int stream, int eq_set) {
+    OHS_CHECK_HANDLE(h);
+    if (eq_set < 0 || eq_set >= h->cfg.n_eq_sets) return fail(OHS_ERR_INVALID, "eq_set %d out of range", eq_set);
+    if (stream != OHS_ALL && (stream < 0 || stream >= h->cfg.n_streams)) return fail(OHS_ERR_INVALID, "stream %d out of range", stream);
+    if (stream == OHS_ALL) std::fill(h->h_stream_eq.begin(), h->h_stream_eq.end(), eq_set);
+    else h->h_stream_eq[stream] = eq_set;
+    h->bind_dirty = true;
+    return OHS_OK;
+}
+
+int ohs_eq_reset(ohs_engine* h) {
+    OHS_CHECK_HANDLE(h);
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    OHS_CUDA(cudaMemsetAsync(h->d_eqs, 0, sizeof(float4) * (size_t)h->cfg.n_streams * kMaxBands, h->stream));
+    return OHS_OK;
+}
+
+int ohs_eq_frequency_response(ohs_engine* h, int eq_set, const float* freqs, float* out, size_t n) {
+    OHS_CHECK_HANDLE(h);
+    if (eq_set < 0 || eq_set >= h->cfg.n_eq_sets || !freqs || !out) return fail(OHS_ERR_INVALID, "bad argument");
+    const float fs = h->cfg.sample_rate;
+    for (size_t i = 0; i < n; ++i) {
+        float rr = 1.0f, ri = 0.0f;
+        for (int b = 0; b < h->cfg.n_bands; ++b) {
+            const float* c = h->h_eqc.data() + ((size_t)eq_set * kMaxBands + b) * kEqCoefStride;
+            if (c[5] == 0.0f) continue;
+            const float w = 2.0f * 3.14159265358979323846f * freqs[i] / fs;
+            const float c1 = cosf(w), s1 = sinf(w), c2 = cosf(2.0f * w), s2 = sinf(2.0f * w);
+            const float nr = c[0] + c[1] * c1 + c[2] * c2, ni = c[1] * s1 + c[2] * s2;
+            const float dr = 1.0f + c[3] * c1 + c[4] * c2, di = c[3] * s1 + c[4] * s2;
+            const float den = dr * dr + di * di;
+            const float hr = (nr * dr + ni * di) / den, hi = (ni * dr - nr * di) / den;
+            const float tr = rr * hr - ri * hi, ti = rr * hi + ri * hr;
+            rr = tr; ri = ti;
+        }
+        out[i] = hypotf(rr, ri);
+    }
+    return OHS_OK;
+}
+
+// ---- switches -----------------------------------------------------------------------------------------------
+int ohs_set_eq_enable(ohs_engine* h, int enable) { OHS_CHECK_HANDLE(h); h->eq_enable = enable ? 1 : 0; return OHS_OK; }
+int ohs_set_conv_enable(ohs_engine* h, int enable) { OHS_CHECK_HANDLE(h); h->conv_enable = enable ? 1 : 0; return OHS_OK; }
+int ohs_set_bypass(ohs_engine* h, int bypass) { OHS_CHECK_HANDLE(h); h->bypass = bypass ? 1 : 0; return OHS_OK; }
+
+int ohs_set_gain(ohs_engine* h, int stream, float gain) {
+    OHS_CHECK_HANDLE(h);
+    if (stream != OHS_ALL && (stream < 0 || stream >= h->cfg.n_streams)) return fail(OHS_ERR_INVALID, "stream %d out of range", stream);
+    if (stream == OHS_ALL) std::fill(h->h_gain.begin(), h->h_gain.end(), gain);
+    else h->h_gain[stream] = gain;
+    h->gain_dirty = true;
+    return OHS_OK;
+}
+
+int ohs_conv_reset(ohs_engine* h) {
+    OHS_CHECK_HANDLE(h);
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    h->head = 0;
+    return clear_history(h, false);
+}
+
+// ---- processing ---------------------------------------------------------------------------------------------
+int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_frames, size_t row_stride) {
+    OHS_CHECK_HANDLE(h);
+    int rc = check_audio_args(h, d_in, d_out, n_frames, row_stride, true);
+    if (rc) return rc;
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    if (n_frames == 0) return OHS_OK;
+    if (h->bypass) {  // master_bypass: buffer untouched, no state advances (src/lib.rs:1169)
+        if (d_in != d_out)
+            OHS_CUDA(cudaMemcpy2DAsync(d_out, row_stride * sizeof(float), d_in, row_stride * sizeof(float), n_frames * sizeof(float),
+                                       (size_t)h->cfg.n_streams * 2, cudaMemcpyDeviceToDevice, h->stream));
+        return OHS_OK;
+    }
+    rc = commit_filters(h);
+    if (rc) return rc;
+    RenderParams p{};
+    p.in = d_in; p.out = d_out; p.row_stride = (long long)row_stride;
+    p.n_blocks = (int)((n_frames + h->B - 1) / h->B);
+    p.tail_frames = (int)(n_frames - (size_t)(p.n_blocks - 1) * h->B);
+    p.n_streams = h->cfg.n_streams;
+    p.stream_hrir = h->d_stream_hrir; p.stream_eq = h->d_stream_eq; p.stream_gain = h->d_stream_gain;
+    p.filt = h->d_filt; p.set_parts = h->d_set_parts; p.fdl = h->d_fdl; p.prev = h->d_prev;
+    p.eqc = h->d_eqc; p.eqs = h->d_eqs; p.tw = h->d_tw;
+    p.pmax = h->pmax; p.head = h->head; p.n_bands = h->cfg.n_bands;
+    p.eq_enable = h->eq_enable && h->cfg.n_bands > 0; p.conv_enable = h->conv_enable;
+    volatile float one = 1.0f;
+    p.one = one;
+    OHS_CUDA(cudaEventRecord(h->ev_k0, h->stream));
+    rc = launch_render(h, p);
+    if (rc) return rc;
+    OHS_CUDA(cudaEventRecord(h->ev_k1, h->stream));
+    h->timed = true;
+    if (h->conv_enable) h->head = (int)(((size_t)h->head + p.n_blocks) % (size_t)h->pmax);
+    return OHS_OK;
+}
+
+int ohs_sync(ohs_engine* h) {
+    OHS_CHECK_HANDLE(h);
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    OHS_CUDA(cudaStreamSynchronize(h->stream));
+    return OHS_OK;
+}
+
+int ohs_cuda_stream(ohs_engine* h, void** stream) {
+    OHS_CHECK_HANDLE(h);
+    if (!stream) return fail(OHS_ERR_INVALID, "null output");
+    *stream = (void*)h->stream;
+    return OHS_OK;
+}
+
+int ohs_launch_count(ohs_engine* h, uint64_t* out) {
+    OHS_CHECK_HANDLE(h);
+    if (!out) return fail(OHS_ERR_INVALID, "null output");
+    *out = h->launches;
+    return OHS_OK;
+}
+
+int ohs_last_kernel_ms(ohs_engine* h, float* ms) {
+    OHS_CHECK_HANDLE(h);
+    if (!ms) return fail(OHS_ERR_INVALID, "null output");
+    if (!h->timed) return fail(OHS_ERR_INVALID, "no kernel has been launched yet");
+    OHS_CUDA(cudaEventSynchronize(h->ev_k1));
+    OHS_CUDA(cudaEventElapsedTime(ms, h->ev_k0, h->ev_k1));
+    return OHS_OK;
+}
+
+int ohs_host_alloc(void** p, size_t bytes) {
+    if (!p) return fail(OHS_ERR_INVALID, "null output");
+    OHS_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return OHS_OK;
+}
+
+int ohs_host_free(void* p) {
+    if (p) OHS_CUDA(cudaFreeHost(p));
+    return OHS_OK;
+}
+
+// Host-pointer flavour: time chunks are staged through three HBM buffers; copy-in, kernel and copy-out of
+// consecutive chunks overlap on three CUDA streams.
+int ohs_process(ohs_engine* h, const float* in, float* out, size_t n_frames, size_t row_stride) {
+    OHS_CHECK_HANDLE(h);
+    int rc = check_audio_args(h, in, out, n_frames, row_stride, false);
+    if (rc) return rc;
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    if (n_frames == 0) return OHS_OK;
+    const size_t rows = (size_t)h->cfg.n_streams * 2;
+    if (h->bypass) {
+        if (in != out) for (size_t r = 0; r < rows; ++r) memcpy(out + r * row_stride, in + r * row_stride, n_frames * sizeof(float));
+        return OHS_OK;
+    }
+    // chunk: whole blocks, about 48 MiB per staging buffer, at least one block
+    const size_t target_bytes = (size_t)48 << 20;
+    size_t chunk = target_bytes / (rows * sizeof(float));
+    chunk = std::max<size_t>(h->B, (chunk / h->B) * h->B);
+    chunk = std::min(chunk, (n_frames + 3) / 4 * 4);
+    if (chunk > h->stage_frames) {
+        for (int i = 0; i < kPipe; ++i) {
+            if (h->d_stage[i]) OHS_CUDA(cudaFree(h->d_stage[i]));
+            h->d_stage[i] = nullptr;
+            OHS_CUDA(cudaMalloc(&h->d_stage[i], rows * chunk * sizeof(float)));
+        }
+        h->stage_frames = chunk;
+    }
+    rc = commit_filters(h);
+    if (rc) return rc;
+    OHS_CUDA(cudaStreamSynchronize(h->stream));
+    size_t done = 0;
+    int idx = 0;
+    bool used[kPipe] = {false, false, false};
+    while (done < n_frames) {
+        const size_t n = std::min(chunk, n_frames - done);
+        const size_t pitch = (n + 3) / 4 * 4;  // device rows stay 16-byte aligned for a ragged EQ-only tail
+        const int b = idx % kPipe;
+        if (used[b]) OHS_CUDA(cudaStreamWaitEvent(h->h2d, h->ev_out[b], 0));  // buffer free once its copy-out finished
+        OHS_CUDA(cudaMemcpy2DAsync(h->d_stage[b], pitch * sizeof(float), in + done, row_stride * sizeof(float), n * sizeof(float), rows,
+                                   cudaMemcpyHostToDevice, h->h2d));
+        OHS_CUDA(cudaEventRecord(h->ev_in[b], h->h2d));
+        OHS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+        rc = ohs_process_device(h, h->d_stage[b], h->d_stage[b], n, pitch);
+        if (rc) return rc;
+        OHS_CUDA(cudaEventRecord(h->ev_comp[b], h->stream));
+        OHS_CUDA(cudaStreamWaitEvent(h->d2h, h->ev_comp[b], 0));
+        OHS_CUDA(cudaMemcpy2DAsync(out + done, row_stride * sizeof(float), h->d_stage[b], pitch * sizeof(float), n * sizeof(float), rows,
+                                   cudaMemcpyDeviceToHost, h->d2h));
+        OHS_CUDA(cudaEventRecord(h->ev_out[b], h->d2h));
+        used[b] = true;
+        done += n;
+        ++idx;
+    }
+    OHS_CUDA(cudaStreamSynchronize(h->d2h));
+    OHS_CUDA(cudaStreamSynchronize(h->stream));
+    return OHS_OK;
+}
+
+// The reference's FIFO adaptation around whole engine blocks (src/dsp/convolution.rs:141-182): append the host block,
+// run every complete engine block, hand back n frames if that many are ready, else silence (and keep what is queued).
+int ohs_process_fifo(ohs_engine* h, const float* in, float* out, size_t n_frames, size_t row_stride) {
+    OHS_CHECK_HANDLE(h);
+    if (!in || !out) return fail(OHS_ERR_INVALID, "null audio pointer");
+    if (row_stride < n_frames) return fail(OHS_ERR_INVALID, "row_stride %zu < n_frames %zu", row_stride, n_frames);
+    const size_t rows = (size_t)h->cfg.n_streams * 2;
+    if (h->bypass) {
+        if (in != out) for (size_t r = 0; r < rows; ++r) memcpy(out + r * row_stride, in + r * row_stride, n_frames * sizeof(float));
+        return OHS_OK;
+    }
+    const size_t need = std::max(h->fifo_in_len, h->fifo_out_len) + n_frames + (size_t)h->B;
+    if (need > h->fifo_cap) {
+        const size_t cap = std::max(need, h->fifo_cap * 2);
+        std::vector<float> ni(rows * cap, 0.f), no(rows * cap, 0.f);
+        for (size_t r = 0; r < rows; ++r) {
+            if (h->fifo_in_len) memcpy(&ni[r * cap], &h->fifo_in[r * h->fifo_cap], h->fifo_in_len * sizeof(float));
+            if (h->fifo_out_len) memcpy(&no[r * cap], &h->fifo_out[r * h->fifo_cap], h->fifo_out_len * sizeof(float));
+        }
+        h->fifo_in.swap(ni); h->fifo_out.swap(no); h->fifo_cap = cap;
+    }
+    const size_t cap = h->fifo_cap;
+    for (size_t r = 0; r < rows; ++r) memcpy(&h->fifo_in[r * cap + h->fifo_in_len], in + r * row_stride, n_frames * sizeof(float));
+    h->fifo_in_len += n_frames;
+    const size_t whole = (h->fifo_in_len / h->B) * h->B;
+    if (whole) {
+        // EQ runs inside the engine on the same whole blocks; in the reference the EQ sees the host buffer before the
+        // FIFO (src/lib.rs:1194-1199) — per-sample filtering, so the result is identical.
+        std::vector<float> tmp(rows * whole);
+        for (size_t r = 0; r < rows; ++r) memcpy(&tmp[r * whole], &h->fifo_in[r * cap], whole * sizeof(float));
+        int rc = ohs_process(h, tmp.data(), tmp.data(), whole, whole);
+        if (rc) return rc;
+        for (size_t r = 0; r < rows; ++r) {
+            memcpy(&h->fifo_out[r * cap + h->fifo_out_len], &tmp[r * whole], whole * sizeof(float));
+            memmove(&h->fifo_in[r * cap], &h->fifo_in[r * cap + whole], (h->fifo_in_len - whole) * sizeof(float));
+        }
+        h->fifo_in_len -= whole;
+        h->fifo_out_len += whole;
+    }
+    if (h->fifo_out_len >= n_frames) {
+        for (size_t r = 0; r < rows; ++r) {
+            memcpy(out + r * row_stride, &h->fifo_out[r * cap], n_frames * sizeof(float));
+            memmove(&h->fifo_out[r * cap], &h->fifo_out[r * cap + n_frames], (h->fifo_out_len - n_frames) * sizeof(float));
+        }
+        h->fifo_out_len -= n_frames;
+    } else {
+        for (size_t r = 0; r < rows; ++r) memset(out + r * row_stride, 0, n_frames * sizeof(float));  // :176-181
+    }
+    return OHS_OK;
+}
+
+// ---- state export / import ----------------------------------------------------------------------------------
+int ohs_state_bytes(ohs_engine* h, size_t* bytes) {
+    OHS_CHECK_HANDLE(h);
+    if (!bytes) return fail(OHS_ERR_INVALID, "null output");
+    const size_t S = h->cfg.n_streams;
+    *bytes = 16 + sizeof(float2) * S * h->pmax * h->N + sizeof(float2) * S * h->B + sizeof(float4) * S * kMaxBands;
+    return OHS_OK;
+}
+
+int ohs_state_export(ohs_engine* h, void* host_buf, size_t bytes) {
+    OHS_CHECK_HANDLE(h);
+    size_t need = 0;
+    ohs_state_bytes(h, &need);
+    if (!host_buf || bytes < need) return fail(OHS_ERR_INVALID, "state buffer too small (%zu < %zu)", bytes, need);
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc = commit_filters(h);
+    if (rc) return rc;
+    OHS_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned char* p = (unsigned char*)host_buf;
+    const size_t S = h->cfg.n_streams;
+    int32_t hdr[4] = {OHS_ABI_VERSION, h->head, h->pmax, h->B};
+    memcpy(p, hdr, 16); p += 16;
+    const size_t n0 = sizeof(float2) * S * h->pmax * h->N, n1 = sizeof(float2) * S * h->B, n2 = sizeof(float4) * S * kMaxBands;
+    OHS_CUDA(cudaMemcpy(p, h->d_fdl, n0, cudaMemcpyDeviceToHost)); p += n0;
+    OHS_CUDA(cudaMemcpy(p, h->d_prev, n1, cudaMemcpyDeviceToHost)); p += n1;
+    OHS_CUDA(cudaMemcpy(p, h->d_eqs, n2, cudaMemcpyDeviceToHost));
+    return OHS_OK;
+}
+
+int ohs_state_import(ohs_engine* h, const void* host_buf, size_t bytes) {
+    OHS_CHECK_HANDLE(h);
+    size_t need = 0;
+    ohs_state_bytes(h, &need);
+    if (!host_buf || bytes < need) return fail(OHS_ERR_INVALID, "state buffer too small (%zu < %zu)", bytes, need);
+    const unsigned char* p = (const unsigned char*)host_buf;
+    int32_t hdr[4];
+    memcpy(hdr, p, 16); p += 16;
+    if (hdr[0] != OHS_ABI_VERSION || hdr[2] != h->pmax || hdr[3] != h->B) return fail(OHS_ERR_INVALID, "state blob does not match this engine's geometry");
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc = commit_filters(h);  // pending set_ir would otherwise clear the imported history later
+    if (rc) return rc;
+    OHS_CUDA(cudaStreamSynchronize(h->stream));
+    const size_t S = h->cfg.n_streams;
+    const size_t n0 = sizeof(float2) * S * h->pmax * h->N, n1 = sizeof(float2) * S * h->B, n2 = sizeof(float4) * S * kMaxBands;
+    h->head = hdr[1];
+    OHS_CUDA(cudaMemcpy(h->d_fdl, p, n0, cudaMemcpyHostToDevice)); p += n0;
+    OHS_CUDA(cudaMemcpy(h->d_prev, p, n1, cudaMemcpyHostToDevice)); p += n1;
+    OHS_CUDA(cudaMemcpy(h->d_eqs, p, n2, cudaMemcpyHostToDevice));
+    return OHS_OK;
+}
+
+}  // extern "C"

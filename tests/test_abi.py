@@ -1,0 +1,109 @@
+"""CPU-side checks of the drop-in boundary: libohs_cuda.so builds (nvcc cross-compiles sm_100a without a GPU), loads,
+exports every symbol include/ohs.h declares, and its pure-host entry points behave.  No GPU compute here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import open_headstage_b200 as ohs
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "ohs.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(ohs_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib = ohs.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), "libohs_cuda.so does not export " + name
+    bound = {s[0] for s in ohs.SYMBOLS}
+    assert set(declared) == bound, set(declared) ^ bound
+    assert lib.ohs_abi_version() == 1
+
+
+def test_library_is_sm100a_and_uses_packed_fp32():
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib_path = os.path.join(ROOT, "open-headstage_b200", "libohs_cuda.so")
+    elf = subprocess.run([cuobjdump, "-lelf", lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run([cuobjdump, "-sass", lib_path], capture_output=True, text=True).stdout
+    # the EQ runs on the packed FP32 pipe: FMUL2 for the five products, FFMA2 (by an opaque 1.0) for the four sums
+    assert "FMUL2" in sass and "FFMA2" in sass
+    assert "LDGSTS" in sass  # cp.async input staging
+
+
+@pytest.mark.parametrize("t", range(8))
+def test_eq_design_bit_identical_to_oracle(t):
+    """ohs_eq_design (product, host) and oracle_eq_design (checker) are separate implementations of biquad 0.4.2
+    from_params; they must agree to the bit so that the GPU engine and the oracle filter with identical coefficients."""
+    rng = np.random.default_rng(t)
+    for _ in range(200):
+        fs = float(rng.choice([44100.0, 48000.0, 96000.0]))
+        fc = float(np.float32(rng.uniform(20.0, 20000.0)))
+        q = float(np.float32(rng.uniform(0.1, 10.0)))
+        g = float(np.float32(rng.uniform(-16.0, 16.0)))
+        a = ohs.eq_design(t, fs, fc, q, g)
+        b = O.eq_design(t, fs, fc, q, g)
+        assert a.tobytes() == b.tobytes(), (t, fs, fc, q, g, a, b)
+
+
+def test_eq_design_errors():
+    with pytest.raises(ohs.OhsError) as e:
+        ohs.eq_design(ohs.PEAK, 48000.0, 30000.0, 1.0, 0.0)
+    assert e.value.code == -4
+    with pytest.raises(ohs.OhsError) as e:
+        ohs.eq_design(ohs.PEAK, 48000.0, 1000.0, -0.5, 0.0)
+    assert e.value.code == -5
+    with pytest.raises(ohs.OhsError) as e:
+        ohs.eq_design(42, 48000.0, 1000.0, 1.0, 0.0)
+    assert e.value.code == -1
+
+
+def test_create_validates_arguments_without_a_gpu():
+    lib = ohs.load_library()
+    h = C.c_void_p()
+    from open_headstage_b200.engine import _Config
+
+    bad = _Config(1, 300, 256, 10, 1, 1, 0, 48000.0)  # block not a supported power of two
+    assert lib.ohs_create(C.byref(bad), C.byref(h)) == -1
+    assert b"block" in lib.ohs_last_error()
+    bad = _Config(0, 256, 256, 10, 1, 1, 0, 48000.0)
+    assert lib.ohs_create(C.byref(bad), C.byref(h)) == -1
+    bad = _Config(1, 256, 256, 11, 1, 1, 0, 48000.0)
+    assert lib.ohs_create(C.byref(bad), C.byref(h)) == -1
+    assert lib.ohs_set_ir(None, 0, 0, None, 0) == -1
+    assert lib.ohs_destroy(None) == 0
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ohs.OhsError) as e:
+        ohs.Engine(1, 256, 256)
+    assert e.value.code == -3
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "open-headstage_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                bad = re.search(r"(import\s+oracle|from\s+oracle|from\s+\.+oracle|ohs_oracle|libohs_oracle|oracle/)", txt)
+                assert not bad, (os.path.join(dirpath, f), bad.group(0))

@@ -1,0 +1,417 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against the CPU oracle
+on identical seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * EQ stage: BIT-EXACT against the oracle's sequential f32 DF2T cascade.
+  * convolution / whole chain: max abs error <= 1e-5 of full scale (inputs peak-normalised to 1.0), EQ compared from
+    the same zero state.
+"""
+import numpy as np
+import pytest
+import scipy.signal as sps
+
+import open_headstage_b200 as ohs
+from open_headstage_b200 import signals as S
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # north_star: max abs error <= 1e-5 full scale (-100 dBFS)
+FS = 48000.0
+
+
+def preset_coeffs(preset, fs=FS):
+    return np.stack([ohs.eq_design(t, fs, fc, q, g) for (t, fc, q, g) in preset])
+
+
+def oracle_render(x, block, irs, coeffs=None, enabled=None, gain=1.0, host_block=None):
+    eq_on = coeffs is not None
+    if coeffs is None:
+        coeffs, enabled = np.zeros((1, 5), np.float32), [0]
+    y, _ = O.render_batch(x, block, irs, coeffs, enabled, eq_on, gain, host_block=host_block, n_threads=8)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the reference's own unit tests, replayed through the mirror objects on the GPU
+# ------------------------------------------------------------------------------------------------------------
+def test_ref_identity_ir_passthrough():
+    """src/dsp/convolution.rs:317-347"""
+    e = ohs.ConvolutionEngine(512)
+    e.set_ir(ohs.LSL, [1.0]); e.set_ir(ohs.LSR, [0.0]); e.set_ir(ohs.RSL, [0.0]); e.set_ir(ohs.RSR, [1.0])
+    i = np.arange(512, dtype=np.float32)
+    in_l = np.sin(i * np.float32(0.1)).astype(np.float32)
+    in_r = np.sin(i * np.float32(-0.1)).astype(np.float32)
+    e.process_block(in_l, in_r)
+    out_l, out_r = e.process_block(in_l, in_r)
+    assert np.max(np.abs(out_l - in_l)) < 1e-3 and np.max(np.abs(out_r - in_r)) < 1e-3
+    assert np.max(np.abs(out_l - in_l)) < 1e-6  # and far inside the reference's own tolerance
+
+
+def test_ref_delay_ir():
+    """src/dsp/convolution.rs:349-383"""
+    e = ohs.ConvolutionEngine(512)
+    ir = np.zeros(6, np.float32); ir[5] = 1.0
+    e.set_ir(ohs.LSL, ir); e.set_ir(ohs.LSR, [0.0]); e.set_ir(ohs.RSL, [0.0]); e.set_ir(ohs.RSR, [0.0])
+    in_l = np.arange(1024, dtype=np.float32)
+    out_l, out_r = e.process_block(in_l, np.zeros(1024, np.float32))
+    expected = np.zeros_like(in_l); expected[5:] = in_l[:-5]
+    assert np.max(np.abs(out_l[5:] - expected[5:])) < 1e-3
+    assert np.max(np.abs(out_r)) < 1e-3
+
+
+def test_ref_long_ir_partitioning():
+    """src/dsp/convolution.rs:385-421"""
+    e = ohs.ConvolutionEngine(512)
+    ir = np.zeros(768, np.float32); ir[0] = 1.0; ir[-1] = 0.5
+    e.set_ir(ohs.LSL, ir)
+    assert e.num_partitions(ohs.LSL) == 2
+    in_l = np.zeros(1536, np.float32); in_l[0] = 1.0
+    out_l, _ = e.process_block(in_l, np.zeros_like(in_l))
+    expected = np.zeros_like(in_l); expected[0] = 1.0; expected[767] = 0.5
+    assert np.max(np.abs(out_l[:768] - expected[:768])) < 1e-3
+
+
+def test_ref_biquad_passthrough_when_disabled():
+    """src/dsp/parametric_eq.rs:218-225 (assert_eq: exact)"""
+    q = ohs.StereoParametricEQ(1, FS)
+    l, r = q.process_block([0.5], [0.5])
+    assert l[0] == np.float32(0.5) and r[0] == np.float32(0.5)
+
+
+def test_ref_biquad_processes_when_enabled():
+    """src/dsp/parametric_eq.rs:227-238"""
+    q = ohs.StereoParametricEQ(1, FS)
+    q.update_band_coeffs(0, FS, ohs.BandConfig(ohs.LOWPASS, 1000.0, 0.707, 0.0, True))
+    l, _ = q.process_block([0.5], [0.5])
+    assert l[0] != np.float32(0.5)
+    ql = O.StereoParametricEQ(1, FS)
+    ql.update_band_coeffs(0, FS, O.LOWPASS, 1000.0, 0.707, 0.0, True)
+    assert l[0] == ql.process_block([0.5], [0.5])[0][0]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# EQ: bit-exact
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("preset_name", ["typical", "harsh"])
+@pytest.mark.parametrize("n_streams,block,n_frames", [(1, 256, 4096), (7, 128, 3000), (4, 512, 5120), (3, 64, 1000)])
+def test_eq_bit_exact(preset_name, n_streams, block, n_frames):
+    preset = S.EQ_PRESET_TYPICAL if preset_name == "typical" else S.EQ_PRESET_HARSH
+    coeffs = preset_coeffs(preset)
+    x = S.stream_inputs(n_streams, n_frames, base_seed=50)
+    e = ohs.Engine(n_streams, block, 1)
+    e.set_conv_enable(False); e.set_eq_enable(True)
+    for b in range(10):
+        e.eq_set_band(b, coeffs[b], True)
+    y = e.process(x)
+    for s in range(n_streams):
+        q = O.StereoParametricEQ(10, FS)
+        for b in range(10):
+            q.set_band_raw(b, coeffs[b], True)
+        l, r = q.process_block(x[s, 0], x[s, 1])
+        assert y[s, 0].tobytes() == l.tobytes(), "stream %d left differs (max %g)" % (s, np.max(np.abs(y[s, 0] - l)))
+        assert y[s, 1].tobytes() == r.tobytes()
+    assert np.isfinite(y).all()
+
+
+def test_eq_state_carries_across_calls_and_resets():
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL)
+    x = S.stream_inputs(2, 2000, base_seed=70)
+    e = ohs.Engine(2, 256, 1)
+    e.set_conv_enable(False); e.set_eq_enable(True)
+    for b in range(10):
+        e.eq_set_band(b, coeffs[b], b != 4)  # one band disabled: exact skip, state untouched (:118-120)
+    whole = e.process(x)
+    e.eq_reset()
+    parts = np.concatenate([e.process(x[:, :, a:a + 333]) for a in range(0, 2000, 333)], axis=2)
+    assert parts.tobytes() == whole.tobytes()
+    q = O.StereoParametricEQ(10, FS)
+    for b in range(10):
+        q.set_band_raw(b, coeffs[b], b != 4)
+    l, r = q.process_block(x[1, 0], x[1, 1])
+    assert whole[1, 0].tobytes() == l.tobytes() and whole[1, 1].tobytes() == r.tobytes()
+
+
+def test_eq_disabled_engine_switch_is_exact_passthrough():
+    x = S.stream_inputs(2, 512, base_seed=80)
+    e = ohs.Engine(2, 256, 1)
+    e.set_conv_enable(False); e.set_eq_enable(False)
+    e.eq_set_preset(S.EQ_PRESET_TYPICAL)
+    assert e.process(x).tobytes() == x.tobytes()
+
+
+def test_eq_sets_bound_per_stream():
+    ca, cb = preset_coeffs(S.EQ_PRESET_TYPICAL), preset_coeffs(S.EQ_PRESET_HARSH)
+    x = S.stream_inputs(5, 1024, base_seed=90)
+    e = ohs.Engine(5, 256, 1, n_eq_sets=2)
+    e.set_conv_enable(False); e.set_eq_enable(True)
+    for b in range(10):
+        e.eq_set_band(b, ca[b], True, eq_set=0)
+        e.eq_set_band(b, cb[b], True, eq_set=1)
+    for s in (1, 3):
+        e.bind_stream_eq(s, 1)
+    y = e.process(x)
+    for s in range(5):
+        q = O.StereoParametricEQ(10, FS)
+        c = cb if s in (1, 3) else ca
+        for b in range(10):
+            q.set_band_raw(b, c[b], True)
+        l, _ = q.process_block(x[s, 0], x[s, 1])
+        assert y[s, 0].tobytes() == l.tobytes()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# convolution: <= 1e-5 against the oracle (and against f64 truth)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("block,taps,n_streams,n_blocks", [
+    (64, 200, 2, 20), (128, 512, 5, 16), (256, 256, 7, 12), (256, 100, 3, 8), (512, 200, 2, 10), (512, 1500, 4, 9),
+    (1024, 5000, 2, 8), (1024, 1024, 1, 5),
+])
+def test_conv_parity(block, taps, n_streams, n_blocks):
+    h = S.synthetic_hrir_set(taps, taps / 6.0, seed=11)
+    n = block * n_blocks
+    x = S.stream_inputs(n_streams, n, base_seed=200)
+    e = ohs.Engine(n_streams, block, taps, n_bands=0)
+    e.set_hrir_set(h)
+    for p in range(4):
+        assert e.num_partitions(p) == -(-taps // block)
+    y = e.process(x)
+    ref = oracle_render(x, block, h)
+    err = float(np.max(np.abs(y - ref)))
+    assert err <= TOL, err
+    # f64 truth for stream 0
+    h64 = h.astype(np.float64)
+    tl = (sps.fftconvolve(x[0, 0].astype(np.float64), h64[0]) + sps.fftconvolve(x[0, 1].astype(np.float64), h64[2]))[:n]
+    assert np.max(np.abs(y[0, 0] - tl)) <= TOL
+
+
+def test_conv_block_at_a_time_equals_one_long_call():
+    """K = 1 launches (the per-block API) and one K = 12 launch walk the same state: identical bits."""
+    h = S.synthetic_hrir_set(900, 150.0, seed=3)
+    x = S.stream_inputs(4, 256 * 12, base_seed=300)
+    a = ohs.Engine(4, 256, 900, n_bands=0); a.set_hrir_set(h)
+    b = ohs.Engine(4, 256, 900, n_bands=0); b.set_hrir_set(h)
+    whole = a.process(x)
+    parts = np.concatenate([b.process(x[:, :, i:i + 256]) for i in range(0, x.shape[2], 256)], axis=2)
+    assert whole.tobytes() == parts.tobytes()
+
+
+def test_default_ir_is_silence_and_empty_ir_mutes():
+    x = S.stream_inputs(2, 1024, base_seed=310)
+    e = ohs.Engine(2, 256, 256, n_bands=0)
+    assert not e.process(x).any()                 # ConvolutionPathData::new: zeros (:46-48)
+    e.set_ir(ohs.LSL, [1.0]); e.set_ir(ohs.RSR, [1.0])
+    assert np.max(np.abs(e.process(x) - x)) < 1e-6
+    e.set_ir(ohs.LSL, []); e.set_ir(ohs.RSR, [])  # empty slice -> one silent partition (:114-118)
+    assert e.num_partitions(ohs.LSL) == 1
+    assert not e.process(x).any()
+
+
+def test_set_ir_clears_history():
+    """set_ir re-creates the ring and zeroes the overlap (:135-138): output restarts as from a fresh engine."""
+    h = S.synthetic_hrir_set(700, 100.0, seed=5)
+    x = S.stream_inputs(2, 2048, base_seed=320)
+    e = ohs.Engine(2, 256, 700, n_bands=0); e.set_hrir_set(h)
+    e.process(x)
+    e.set_hrir_set(h)
+    again = e.process(x)
+    fresh = ohs.Engine(2, 256, 700, n_bands=0); fresh.set_hrir_set(h)
+    assert again.tobytes() == fresh.process(x).tobytes()
+
+
+def test_hrir_sets_bound_per_stream_and_ear_routing():
+    """out_l = LSL + RSL, out_r = LSR + RSR (:229-230); streams pick their set."""
+    ha = S.synthetic_hrir_set(256, 40.0, seed=7)
+    hb = S.synthetic_hrir_set(300, 60.0, seed=8)
+    x = S.stream_inputs(6, 256 * 6, base_seed=330)
+    e = ohs.Engine(6, 256, 300, n_bands=0, n_hrir_sets=2)
+    e.set_hrir_set(ha, 0); e.set_hrir_set(hb, 1)
+    for s in (0, 2, 5):
+        e.bind_stream_hrir(s, 1)
+    y = e.process(x)
+    for s in range(6):
+        ref = oracle_render(x[s:s + 1], 256, hb if s in (0, 2, 5) else ha)
+        assert np.max(np.abs(y[s] - ref[0])) <= TOL
+    # ear routing with one-hot paths
+    e2 = ohs.Engine(1, 256, 8, n_bands=0)
+    e2.set_ir(ohs.LSR, [0.0, 1.0])  # left speaker -> right ear, delayed by one sample
+    y2 = e2.process(x[:1, :, :512])
+    assert not y2[0, 0].any()
+    assert np.max(np.abs(y2[0, 1, 1:] - x[0, 0, :511])) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the whole chain (EQ -> conv -> gain), BASELINE configs at oracle-sized extents
+# ------------------------------------------------------------------------------------------------------------
+def test_config1_single_stream_sofa_10s(cipic):
+    """cfg 1: one stereo stream, 48 kHz, 10 s pink noise, bundled CIPIC HRIRs (30 deg / 330 deg), 10-band PEQ, block 512."""
+    ir = cipic["ir"]
+    irs = [ir[308, 0], ir[308, 1], ir[908, 0], ir[908, 1]]
+    n = 938 * 512  # 10 s = 480 000 frames, zero-padded to whole blocks
+    x = np.zeros((1, 2, n), np.float32)
+    x[0, 0, :480000] = S.pink_noise(480000, 1)
+    x[0, 1, :480000] = S.pink_noise(480000, 2)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL)
+    e = ohs.Engine(1, 512, 200)
+    e.set_hrir_set(irs)
+    for b in range(10):
+        e.eq_set_band(b, coeffs[b], True)
+    e.set_eq_enable(True); e.set_gain(0.5)
+    y = e.process(x)
+    ref = oracle_render(x, 512, irs, coeffs, [1] * 10, 0.5)
+    err = float(np.max(np.abs(y - ref)))
+    assert err <= TOL, err
+    assert np.abs(y).max() > 0.1
+
+
+@pytest.mark.parametrize("cfg,n_streams,seconds", [(2, 48, 1.0), (3, 40, 0.5)])
+def test_config2_3_chain_parity(cfg, n_streams, seconds):
+    c = S.CONFIGS[cfg]
+    block, taps = c["block"], c["taps"]
+    h = S.synthetic_hrir_set(taps, c["decay"])
+    n = int(seconds * c["fs"]) // block * block
+    x = S.stream_inputs(n_streams, n)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL, c["fs"])
+    e = ohs.Engine(n_streams, block, taps, sample_rate=c["fs"])
+    e.set_hrir_set(h)
+    e.eq_set_preset(S.EQ_PRESET_TYPICAL)
+    e.set_eq_enable(True); e.set_gain(0.5)
+    y = e.process(x)
+    ref = oracle_render(x, block, h, coeffs, [1] * 10, 0.5)
+    err = float(np.max(np.abs(y - ref)))
+    assert err <= TOL, err
+
+
+def test_config5_long_brir_parity():
+    """cfg 5: 48 000-tap BRIR per path, partition 1024, 96 kHz (47 partitions); 3 streams x 60 blocks."""
+    c = S.CONFIGS[5]
+    h = S.synthetic_hrir_set(c["taps"], c["decay"])
+    n = 1024 * 60
+    x = S.stream_inputs(3, n)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL, c["fs"])
+    e = ohs.Engine(3, 1024, c["taps"], sample_rate=c["fs"])
+    e.set_hrir_set(h)
+    assert e.num_partitions(0) == 47
+    e.eq_set_preset(S.EQ_PRESET_TYPICAL)
+    e.set_eq_enable(True); e.set_gain(0.5)
+    y = np.concatenate([e.process(x[:, :, :1024 * 25]), e.process(x[:, :, 1024 * 25:])], axis=2)
+    ref = oracle_render(x, 1024, h, coeffs, [1] * 10, 0.5)
+    err = float(np.max(np.abs(y - ref)))
+    assert err <= TOL, err
+
+
+def test_bypass_gain_and_order():
+    h = S.synthetic_hrir_set(256, 40.0)
+    x = S.stream_inputs(3, 1024, base_seed=400)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL)
+    e = ohs.Engine(3, 256, 256)
+    e.set_hrir_set(h); e.eq_set_preset(S.EQ_PRESET_TYPICAL); e.set_eq_enable(True)
+    e.set_bypass(True)
+    assert e.process(x).tobytes() == x.tobytes()          # src/lib.rs:1169 buffer untouched, no state advance
+    e.set_bypass(False)
+    e.set_gain(0.5); e.set_gain(0.25, stream=1)
+    y = e.process(x)
+    for s, g in ((0, 0.5), (1, 0.25), (2, 0.5)):
+        ref = oracle_render(x[s:s + 1], 256, h, coeffs, [1] * 10, g)
+        assert np.max(np.abs(y[s] - ref[0])) <= TOL
+
+
+@pytest.mark.parametrize("n", [100, 256, 512, 700])
+def test_fifo_semantics_match_reference(n):
+    """src/dsp/convolution.rs:141-182: zero-filled output while starved, latency 512 - n afterwards."""
+    h = S.synthetic_hrir_set(300, 50.0, seed=9)
+    x = S.stream_inputs(1, n * 9, base_seed=500)
+    g = ohs.ConvolutionEngine(512)
+    o = O.ConvolutionEngine(512)
+    for p in range(4):
+        g.set_ir(p, h[p]); o.set_ir(p, h[p])
+    for i in range(9):
+        seg = x[0, :, i * n:(i + 1) * n]
+        gl, gr = g.process_block(seg[0], seg[1])
+        ol, orr = o.process_block(seg[0], seg[1])
+        assert (not gl.any()) == (not ol.any())
+        assert np.max(np.abs(gl - ol)) <= TOL and np.max(np.abs(gr - orr)) <= TOL
+
+
+def test_state_export_import_resumes_bit_exactly():
+    h = S.synthetic_hrir_set(1000, 200.0, seed=4)
+    x = S.stream_inputs(3, 256 * 10, base_seed=600)
+
+    def make():
+        e = ohs.Engine(3, 256, 1000)
+        e.set_hrir_set(h); e.eq_set_preset(S.EQ_PRESET_TYPICAL); e.set_eq_enable(True); e.set_gain(0.5)
+        return e
+
+    a = make()
+    whole = a.process(x)
+    b = make()
+    first = b.process(x[:, :, :256 * 4])
+    blob = b.state_export()
+    c = make()
+    c.state_import(blob)
+    second = c.process(x[:, :, 256 * 4:])
+    assert np.concatenate([first, second], axis=2).tobytes() == whole.tobytes()
+
+
+def test_device_pointers_stride_and_in_place():
+    import torch
+
+    h = S.synthetic_hrir_set(256, 40.0)
+    x = S.stream_inputs(5, 256 * 8, base_seed=700)
+    e = ohs.Engine(5, 256, 256)
+    e.set_hrir_set(h); e.eq_set_preset(S.EQ_PRESET_TYPICAL); e.set_eq_enable(True); e.set_gain(0.5)
+    want = e.process(x)
+    e.conv_reset(); e.eq_reset()
+    stride = 256 * 8 + 64
+    buf = torch.zeros((5, 2, stride), dtype=torch.float32, device="cuda")
+    buf[:, :, :256 * 8] = torch.from_numpy(x).cuda()
+    torch.cuda.synchronize()
+    n0 = e.launch_count()
+    e.process_device(buf.data_ptr(), buf.data_ptr(), 256 * 8, stride)  # in place, padded rows
+    e.sync()
+    assert e.launch_count() == n0 + 1
+    assert e.last_kernel_ms() > 0
+    got = buf[:, :, :256 * 8].cpu().numpy()
+    assert got.tobytes() == want.tobytes()
+    assert not buf[:, :, 256 * 8:].any()
+
+
+def test_errors_are_codes_not_crashes():
+    e = ohs.Engine(2, 256, 256)
+    with pytest.raises(ohs.OhsError):
+        e.process(np.zeros((2, 2, 100), np.float32))      # not whole blocks -> use process_fifo
+    with pytest.raises(ohs.OhsError):
+        e.set_ir(0, np.zeros(300, np.float32))            # longer than max_taps capacity
+    with pytest.raises(ohs.OhsError):
+        e.set_ir(4, [1.0])
+    with pytest.raises(ohs.OhsError):
+        e.eq_update_band(0, ohs.PEAK, 30000.0, 1.0, 0.0)   # the reference would panic (parametric_eq.rs:111)
+    e.eq_update_band(99, ohs.PEAK, 1000.0, 1.0, 0.0)       # out-of-range band silently ignored (:145)
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 at full width (1024 streams): batch position must not matter — sampled streams equal the same
+    stream rendered alone, bit for bit — and those sampled streams meet the oracle tolerance."""
+    c = S.CONFIGS[2]
+    h = S.synthetic_hrir_set(c["taps"], c["decay"])
+    n = 256 * 40
+    x = S.stream_inputs(1024, n, unique=64)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL)
+    e = ohs.Engine(1024, 256, 256)
+    e.set_hrir_set(h); e.eq_set_preset(S.EQ_PRESET_TYPICAL); e.set_eq_enable(True); e.set_gain(0.5)
+    y = e.process(x)
+    assert np.isfinite(y).all()
+    # tiled inputs -> tiled outputs
+    assert y[:64].tobytes() == y[64:128].tobytes() == y[960:1024].tobytes()
+    for s in (0, 1, 2, 63):
+        solo = ohs.Engine(1, 256, 256)
+        solo.set_hrir_set(h); solo.eq_set_preset(S.EQ_PRESET_TYPICAL); solo.set_eq_enable(True); solo.set_gain(0.5)
+        assert solo.process(x[s:s + 1]).tobytes() == y[s:s + 1].tobytes()
+    ref = oracle_render(x[:8], 256, h, coeffs, [1] * 10, 0.5)
+    assert np.max(np.abs(y[:8] - ref)) <= TOL
+    # linearity of the convolution stage (EQ off): render(a) + render(b) == render(a + b) within round-off
+    lin = ohs.Engine(1024, 256, 256, n_bands=0); lin.set_hrir_set(h)
+    ya = lin.process(x); lin.conv_reset()
+    yb = lin.process(x[::-1].copy()); lin.conv_reset()
+    yab = lin.process(x + x[::-1])
+    assert np.max(np.abs(ya + yb - yab)) <= TOL
