@@ -236,7 +236,8 @@ def test_hrir_sets_bound_per_stream_and_ear_routing():
     e2 = ohs.Engine(1, 256, 8, n_bands=0)
     e2.set_ir(ohs.LSR, [0.0, 1.0])  # left speaker -> right ear, delayed by one sample
     y2 = e2.process(x[:1, :, :512])
-    assert not y2[0, 0].any()
+    # left + i*right share one complex FFT, so the silent ear carries round-off cross-talk (~1e-8), not exact zero
+    assert np.max(np.abs(y2[0, 0])) < 1e-6
     assert np.max(np.abs(y2[0, 1, 1:] - x[0, 0, :511])) < 1e-6
 
 
