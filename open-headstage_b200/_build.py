@@ -38,5 +38,9 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
-        subprocess.check_call(cmd, cwd=ROOT)
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
+        if verbose or r.returncode:
+            print(r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError("nvcc failed building libohs_cuda.so")
     return LIB

@@ -102,6 +102,7 @@ template <int N, int G> int launch_render_ng(ohs_engine* h, const RenderParams& 
     int dev = h->cfg.device;
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         OHS_CUDA(cudaFuncSetAttribute(render_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kBytes));
+        OHS_CUDA(cudaFuncSetAttribute(render_kernel<N, G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[dev] = true;
     }
     const int grid = (p.n_streams + G - 1) / G;

@@ -202,6 +202,12 @@ template <int N, int G> struct RenderSmem {
     static constexpr size_t kRingOff = kZOff + sizeof(float2) * G * 2 * NP;  // float2 ring[G][3][B]
     static constexpr size_t kStageOff = kRingOff + sizeof(float2) * G * 3 * B;  // float stage[2][G][2][B]
     static constexpr size_t kBytes = kStageOff + sizeof(float) * 2 * G * 2 * B;
+    // resident CTAs per SM the register allocation is held to: as many as shared memory and threads allow, up to four,
+    // while leaving each thread at least 80 registers
+    static constexpr int kBySmem = (int)((227 * 1024) / (kBytes + 1024));
+    static constexpr int kByRegs = 65536 / (80 * kThreads);
+    static constexpr int kMinBlocks0 = kBySmem < kByRegs ? kBySmem : kByRegs;
+    static constexpr int kMinBlocks = kMinBlocks0 < 1 ? 1 : (kMinBlocks0 > 4 ? 4 : kMinBlocks0);
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -222,6 +228,71 @@ __device__ __forceinline__ float2 df2t_step(float2 x, float2& s1, float2& s2, fl
     const float2 m4 = __fmul2_rn(na2, out);
     s2 = __ffma2_rn(m4, one, m3);
     return out;
+}
+
+// One engine block through the band-systolic chain of one warp.  Lane (g, j) filters sample n = step - D*j with band
+// j; step runs 0 .. nb-1+9D.  The steady state (every lane busy) is branch-free and unrolled by four; the fill and
+// drain steps (and ragged or partly disabled cases) go through the checked step, which commits state by select.
+// FAST: nb == B and no valid lane is disabled.
+template <int B, bool FAST>
+__device__ __forceinline__ void eq_block_systolic(const float* __restrict__ xl, const float* __restrict__ xr, float2* __restrict__ dst,
+                                                  int nb, int j, int src_lane, bool lane_valid, bool en, float2& s1, float2& s2,
+                                                  float2 b0, float2 b1, float2 b2, float2 na1, float2 na2, float2 one) {
+    static_assert(kEqSkew == 2, "register rotation below is written for a skew of two");
+    [[maybe_unused]] constexpr int D = kEqSkew;
+    constexpr int kLag = (kEqGroup - 1) * D;          // steps until the last band sees sample 0
+    constexpr int kHead = (kLag + 3) / 4 * 4;         // checked steps before the unrolled steady state
+    const bool first = (j == 0), last = (j == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
+    float2 o0 = make_float2(0.f, 0.f), o1 = o0;       // this lane's outputs of the previous two steps (o1 older)
+
+    auto checked_step = [&](int step) {
+        const int n = step - D * j;
+        const bool act = lane_valid && n >= 0 && n < nb;
+        float2 x;
+        x.x = __shfl_sync(0xffffffffu, o1.x, src_lane);
+        x.y = __shfl_sync(0xffffffffu, o1.y, src_lane);
+        const int nc = step < B ? step : B - 1;
+        const float il = xl[nc], ir = xr[nc];
+        x.x = first ? il : x.x;
+        x.y = first ? ir : x.y;
+        float2 t1 = s1, t2 = s2;
+        float2 out = df2t_step(x, t1, t2, b0, b1, b2, na1, na2, one);
+        const bool upd = act && en;
+        s1.x = upd ? t1.x : s1.x; s1.y = upd ? t1.y : s1.y;
+        s2.x = upd ? t2.x : s2.x; s2.y = upd ? t2.y : s2.y;
+        out.x = upd ? out.x : x.x; out.y = upd ? out.y : x.y;
+        if (act && last) dst[n] = out;
+        o1 = o0; o0 = out;
+    };
+
+    if constexpr (!FAST) {
+        for (int step = 0; step < nb + kLag; ++step) checked_step(step);
+    } else {
+#pragma unroll 1
+    for (int step = 0; step < kHead; ++step) checked_step(step);
+    // steady state: every lane holds a live sample; lanes of absent streams compute on garbage that is never stored
+    float2* dlast = dst - kLag;
+#pragma unroll 1
+    for (int step = kHead; step < B; step += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(xl + step);
+        const float4 r4 = *reinterpret_cast<const float4*>(xr + step);
+        const float il[4] = {l4.x, l4.y, l4.z, l4.w};
+        const float ir[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float2 x;
+            x.x = __shfl_sync(0xffffffffu, o1.x, src_lane);
+            x.y = __shfl_sync(0xffffffffu, o1.y, src_lane);
+            x.x = first ? il[u] : x.x;
+            x.y = first ? ir[u] : x.y;
+            const float2 out = df2t_step(x, s1, s2, b0, b1, b2, na1, na2, one);
+            if (last) dlast[step + u] = out;
+            o1 = o0; o0 = out;
+        }
+    }
+#pragma unroll 1
+    for (int step = B; step < B + kLag; ++step) checked_step(step);
+    }
 }
 
 template <int N, int G>
@@ -281,6 +352,8 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     };
 
     const int src_lane = (j == 0) ? lane : lane - 1;
+    // every valid lane filters (no disabled band in this warp): the steady-state loop needs no per-lane selects
+    const bool all_fast = __all_sync(0xffffffffu, en || !lane_valid);
     issue_stage(0);
     for (int t = 0; t < p.n_blocks; ++t) {
         if (t + 1 < p.n_blocks) { issue_stage(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
@@ -299,29 +372,8 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             const float* xl = st_base + (g * 2) * B;
             const float* xr = xl + B;
             float2* dst = ring + (g * 3 + slot) * B;
-            float2 o[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) o[d] = make_float2(0.f, 0.f);
-            for (int step0 = 0; step0 < B + (kEqGroup - 1) * D; step0 += D) {
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    const int step = step0 + d;
-                    const int n = step - D * j;
-                    const bool act = lane_valid && n >= 0 && n < nb;
-                    float2 x;
-                    x.x = __shfl_sync(0xffffffffu, o[D - 1].x, src_lane);
-                    x.y = __shfl_sync(0xffffffffu, o[D - 1].y, src_lane);
-                    if (j == 0) { const int nc = step < B ? step : B - 1; x = make_float2(xl[nc], xr[nc]); }
-                    float2 out = x;
-                    if (act) {
-                        if (en) out = df2t_step(x, s1, s2, b0, b1, b2, na1, na2, one);
-                        if (j == kEqGroup - 1) dst[n] = out;
-                    }
-#pragma unroll
-                    for (int e = D - 1; e > 0; --e) o[e] = o[e - 1];
-                    o[0] = out;
-                }
-            }
+            if (nb == B && all_fast) eq_block_systolic<B, true>(xl, xr, dst, B, j, src_lane, lane_valid, en, s1, s2, b0, b1, b2, na1, na2, one);
+            else eq_block_systolic<B, false>(xl, xr, dst, nb, j, src_lane, lane_valid, en, s1, s2, b0, b1, b2, na1, na2, one);
         }
         __threadfence_block();
         bar_arrive(kBarFull0 + (t & 1), kCount);
@@ -459,7 +511,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
 }
 
 template <int N, int G>
-__global__ void __launch_bounds__(RenderSmem<N, G>::kThreads) render_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(RenderSmem<N, G>::kThreads, RenderSmem<N, G>::kMinBlocks) render_kernel(const RenderParams p) {
     using SM = RenderSmem<N, G>;
     extern __shared__ __align__(16) unsigned char smem[];
     const int stream0 = blockIdx.x * G;
