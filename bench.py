@@ -263,6 +263,8 @@ def run_gpu(args, pkg):
     value = stream_seconds_per_step / (ms_per_step * 1e-3)
 
     if args.device_only:
+        if sampler:
+            sampler.stop()  # a lingering nvidia-smi child would keep ncu (which waits for all children) from exiting
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "gpu_launches": int(launches),
                               "note": "device-only run (profiling helper)"}))

@@ -112,13 +112,22 @@ template <int N, int G> int launch_render_ng(ohs_engine* h, const RenderParams& 
     return OHS_OK;
 }
 
+template <int N, int G> int launch_render_if_fits(ohs_engine* h, const RenderParams& p) {
+    if constexpr (RenderSmem<N, G>::kFits) return launch_render_ng<N, G>(h, p);
+    else return fail(OHS_ERR_INVALID, "%d streams per CTA do not fit for block %d", G, N / 2);
+}
+
 template <int N> int launch_render_n(ohs_engine* h, const RenderParams& p) {
     switch (h->G) {
-        case 1: return launch_render_ng<N, 1>(h, p);
-        case 2: if constexpr (RenderSmem<N, 2>::kBytes <= 227 * 1024) return launch_render_ng<N, 2>(h, p); break;
-        case 3: if constexpr (RenderSmem<N, 3>::kBytes <= 227 * 1024) return launch_render_ng<N, 3>(h, p); break;
+        case 1: return launch_render_if_fits<N, 1>(h, p);
+        case 2: return launch_render_if_fits<N, 2>(h, p);
+        case 3: return launch_render_if_fits<N, 3>(h, p);
+        case 4: return launch_render_if_fits<N, 4>(h, p);
+        case 5: return launch_render_if_fits<N, 5>(h, p);
+        case 6: return launch_render_if_fits<N, 6>(h, p);
+        case 7: return launch_render_if_fits<N, 7>(h, p);
     }
-    return fail(OHS_ERR_INVALID, "unsupported streams-per-CTA %d for block %d", h->G, N / 2);
+    return fail(OHS_ERR_INVALID, "unsupported streams-per-CTA %d", h->G);
 }
 
 int launch_render(ohs_engine* h, const RenderParams& p) {
@@ -132,13 +141,21 @@ int launch_render(ohs_engine* h, const RenderParams& p) {
     return fail(OHS_ERR_INVALID, "unsupported block size %d", h->B);
 }
 
-size_t render_smem_bytes(int N, int G) {
-#define OHS_CASE(n)                                                     \
-    case n:                                                             \
-        return G == 1 ? RenderSmem<n, 1>::kBytes : G == 2 ? RenderSmem<n, 2>::kBytes : RenderSmem<n, 3>::kBytes;
-    switch (N) { OHS_CASE(128) OHS_CASE(256) OHS_CASE(512) OHS_CASE(1024) OHS_CASE(2048) }
-#undef OHS_CASE
-    return ~(size_t)0;
+template <int N> bool render_fits_n(int G) {
+    switch (G) {
+        case 1: return RenderSmem<N, 1>::kFits; case 2: return RenderSmem<N, 2>::kFits; case 3: return RenderSmem<N, 3>::kFits;
+        case 4: return RenderSmem<N, 4>::kFits; case 5: return RenderSmem<N, 5>::kFits; case 6: return RenderSmem<N, 6>::kFits;
+        case 7: return RenderSmem<N, 7>::kFits;
+    }
+    return false;
+}
+
+bool render_fits(int N, int G) {
+    switch (N) {
+        case 128: return render_fits_n<128>(G); case 256: return render_fits_n<256>(G); case 512: return render_fits_n<512>(G);
+        case 1024: return render_fits_n<1024>(G); case 2048: return render_fits_n<2048>(G);
+    }
+    return false;
 }
 
 template <int N> int launch_setup_n(ohs_engine* h, int max_parts, int n_sets) {
@@ -301,17 +318,17 @@ int check_audio_args(ohs_engine* h, const void* in, const void* out, size_t n_fr
 int pick_streams_per_cta(const ohs_engine* h) {
     if (const char* e = getenv("OHS_STREAMS_PER_CTA")) {
         const int g = atoi(e);
-        if (g >= 1 && g <= kMaxG && render_smem_bytes(h->N, g) <= 227 * 1024) return g;
+        if (g >= 1 && g <= kMaxG && render_fits(h->N, g)) return g;
     }
     cudaDeviceProp prop{};
     int sms = 148;
     if (cudaGetDeviceProperties(&prop, h->cfg.device) == cudaSuccess) sms = prop.multiProcessorCount;
-    // fill the EQ warp (3 x 10 lanes) when that still leaves at least one CTA per SM
-    for (int g = kMaxG; g >= 1; --g) {
-        if (render_smem_bytes(h->N, g) > 227 * 1024) continue;
-        if (g == 1 || (h->cfg.n_streams + g - 1) / g >= sms) return g;
-    }
-    return 1;
+    // spread the streams evenly over the SMs: ceil(n_streams / SMs) per CTA (config 2: 1024 streams -> 7 per CTA, 147
+    // CTAs), capped by what fits in one CTA
+    int g = (h->cfg.n_streams + sms - 1) / sms;
+    g = std::max(1, std::min(g, kMaxG));
+    while (g > 1 && !render_fits(h->N, g)) --g;
+    return g;
 }
 
 }  // namespace
@@ -413,9 +430,12 @@ int ohs_create(const ohs_config* cfg, ohs_engine** out) {
     OHS_TRY(cudaMemsetAsync(h->d_ir, 0, sizeof(float) * (size_t)cfg->n_hrir_sets * 4 * per_path, h->stream));
     {
         std::vector<float2> tw(h->N);
-        for (int m = 0; m < h->N; ++m) {
-            const double a = -2.0 * 3.14159265358979323846 * (double)m / (double)h->N;
-            tw[m] = make_float2((float)cos(a), (float)sin(a));
+        switch (h->N) {
+            case 128: fill_twiddles<128>(tw.data()); break;
+            case 256: fill_twiddles<256>(tw.data()); break;
+            case 512: fill_twiddles<512>(tw.data()); break;
+            case 1024: fill_twiddles<1024>(tw.data()); break;
+            case 2048: fill_twiddles<2048>(tw.data()); break;
         }
         OHS_TRY(cudaMemcpyAsync(h->d_tw, tw.data(), sizeof(float2) * h->N, cudaMemcpyHostToDevice, h->stream));
         OHS_TRY(cudaMemcpyAsync(h->d_set_parts, h->h_set_parts.data(), sizeof(int) * cfg->n_hrir_sets, cudaMemcpyHostToDevice, h->stream));
@@ -625,8 +645,7 @@ int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_
     p.eqc = h->d_eqc; p.eqs = h->d_eqs; p.tw = h->d_tw;
     p.pmax = h->pmax; p.head = h->head; p.n_bands = h->cfg.n_bands;
     p.eq_enable = h->eq_enable && h->cfg.n_bands > 0; p.conv_enable = h->conv_enable;
-    volatile float one = 1.0f;
-    p.one = one;
+    p.one = 1.0f;
     OHS_CUDA(cudaEventRecord(h->ev_k0, h->stream));
     rc = launch_render(h, p);
     if (rc) return rc;

@@ -31,11 +31,11 @@ namespace ohs {
 
 constexpr int kMaxBands = 10;
 constexpr int kEqGroup = 10;   // lanes per stream in the EQ warp
-constexpr int kMaxG = 3;       // streams per CTA (3 x 10 lanes fill one warp)
-constexpr int kEqSkew = 2;     // samples between neighbouring bands of the systolic chain (covers SHFL latency)
+constexpr int kMaxG = 7;       // streams per CTA; their 2G channels x 10 bands are spread over ceil(2G/3) EQ warps
+constexpr int kEqSkew = 4;     // samples between neighbouring bands of the systolic chain (hides the 26-cycle SHFL)
 constexpr int kEqCoefStride = 8;  // floats per (eq_set, band): b0 b1 b2 a1 a2 enabled pad pad
 
-enum NamedBarrier { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarStream0 = 5 };
+enum NamedBarrier { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarEq = 5, kBarStream0 = 6 };
 
 struct RenderParams {
     const float* in;            // [stream][2][row_stride]
@@ -77,6 +77,14 @@ __host__ __device__ constexpr int padded_len(int n) { return n + (n >> 3); }
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// AND-reduce a predicate over the first NT threads of the CTA (the EQ warps) on their named barrier
+template <int NT> __device__ __forceinline__ bool __syncthreads_and_eq(bool pred) {
+    unsigned r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.and.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(r) : "r"((unsigned)pred), "r"((int)kBarEq), "r"(NT) : "memory");
+    return r != 0;
+}
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -135,6 +143,14 @@ template <int N, int T> struct FftPlan {
     static constexpr int P4 = P3 * R3, R4 = (P4 < N) ? ((N / P4 >= E) ? E : N / P4) : 1;
     static_assert(P4 * R4 == N, "at most four passes");
     static constexpr int kPasses = 2 + (R3 > 1) + (R4 > 1);
+    // per-pass twiddle tables, laid out [r-1][k] so that lanes with consecutive k read consecutive float2 (no bank
+    // conflicts; a single table indexed k*r*N/(P*R) puts 8 lanes on one bank): pass with radix R after product P
+    // uses entries w^{k r / (P R)}, k < P, r = 1..R-1
+    static constexpr int kTw2 = 0;
+    static constexpr int kTw3 = kTw2 + (R2 - 1) * P2;
+    static constexpr int kTw4 = kTw3 + (R3 > 1 ? (R3 - 1) * P3 : 0);
+    static constexpr int kTwLen = kTw4 + (R4 > 1 ? (R4 - 1) * P4 : 0);
+    static_assert(kTwLen <= N, "twiddle tables fit in N entries");
     static constexpr bool kOutInB0 = (kPasses % 2) == 1;  // which ping-pong buffer a full transform ends in
 };
 
@@ -153,7 +169,7 @@ __device__ __forceinline__ void fft_pass(int tid, const float2* __restrict__ tw,
         for (int r = 0; r < R; ++r) u[r] = load(i + r * NB);
         if (P > 1) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) u[r] = cmul(u[r], tw[(k * r) * (N / (P * R))]);
+            for (int r = 1; r < R; ++r) u[r] = cmul(u[r], tw[(r - 1) * P + k]);
         }
         Dft<R>::run(u);
 #pragma unroll
@@ -175,17 +191,33 @@ __device__ __forceinline__ void fft_run(int tid, const float2* __restrict__ tw, 
     after_first();
     sync();
     if constexpr (Pl::kPasses == 2) {
-        fft_pass<N, T, Pl::R2, Pl::P2>(tid, tw, ld0, store_last);
+        fft_pass<N, T, Pl::R2, Pl::P2>(tid, tw + Pl::kTw2, ld0, store_last);
     } else {
-        fft_pass<N, T, Pl::R2, Pl::P2>(tid, tw, ld0, st1);
+        fft_pass<N, T, Pl::R2, Pl::P2>(tid, tw + Pl::kTw2, ld0, st1);
         sync();
         if constexpr (Pl::kPasses == 3) {
-            fft_pass<N, T, Pl::R3, Pl::P3>(tid, tw, ld1, store_last);
+            fft_pass<N, T, Pl::R3, Pl::P3>(tid, tw + Pl::kTw3, ld1, store_last);
         } else {
-            fft_pass<N, T, Pl::R3, Pl::P3>(tid, tw, ld1, st0);
+            fft_pass<N, T, Pl::R3, Pl::P3>(tid, tw + Pl::kTw3, ld1, st0);
             sync();
-            fft_pass<N, T, Pl::R4, Pl::P4>(tid, tw, ld0, store_last);
+            fft_pass<N, T, Pl::R4, Pl::P4>(tid, tw + Pl::kTw4, ld0, store_last);
         }
+    }
+}
+
+// host side: the per-pass tables for FftPlan<N, T>, f64-computed and rounded once (as rustfft's twiddles are)
+template <int N> inline void fill_twiddles(float2* out) {
+    constexpr int T = (N / 8 >= 32) ? N / 8 : 32;
+    using Pl = FftPlan<N, T>;
+    const int R[3] = {Pl::R2, Pl::R3, Pl::R4}, P[3] = {Pl::P2, Pl::P3, Pl::P4}, off[3] = {Pl::kTw2, Pl::kTw3, Pl::kTw4};
+    for (int i = 0; i < N; ++i) out[i] = make_float2(1.f, 0.f);
+    for (int q = 0; q < 3; ++q) {
+        if (R[q] <= 1) continue;
+        for (int r = 1; r < R[q]; ++r)
+            for (int k = 0; k < P[q]; ++k) {
+                const double a = -2.0 * 3.14159265358979323846 * (double)k * (double)r / ((double)P[q] * (double)R[q]);
+                out[off[q] + (r - 1) * P[q] + k] = make_float2((float)cos(a), (float)sin(a));
+            }
     }
 }
 
@@ -194,191 +226,224 @@ __device__ __forceinline__ void fft_run(int tid, const float2* __restrict__ tw, 
 // ---------------------------------------------------------------------------------------------------------------
 template <int N, int G> struct RenderSmem {
     static constexpr int B = N / 2;
-    static constexpr int T = (N / 8 >= 32) ? N / 8 : 32;
+    static constexpr int T = (N / 8 >= 32) ? N / 8 : 32;   // convolution threads per stream
     static constexpr int NP = padded_len(N);
-    static constexpr int kThreads = 32 + G * T;
+    static constexpr int kEqWarps = (2 * G + 2) / 3;         // three (stream, channel) chains of 10 lanes per EQ warp
+    static constexpr int kEqThreads = 32 * kEqWarps;
+    static constexpr int kThreads = kEqThreads + G * T;
     static constexpr size_t kTwOff = 0;                                      // float2 tw[N]
     static constexpr size_t kZOff = kTwOff + sizeof(float2) * N;             // float2 z[G][2][NP]
-    static constexpr size_t kRingOff = kZOff + sizeof(float2) * G * 2 * NP;  // float2 ring[G][3][B]
-    static constexpr size_t kStageOff = kRingOff + sizeof(float2) * G * 3 * B;  // float stage[2][G][2][B]
-    static constexpr size_t kBytes = kStageOff + sizeof(float) * 2 * G * 2 * B;
-    // resident CTAs per SM the register allocation is held to: as many as shared memory and threads allow, up to four,
-    // while leaving each thread at least 80 registers
+    // per-stream strides carry a 16-byte pad so that neighbouring streams sit on different banks
+    static constexpr int kRingStride = 3 * B + 2;    // float2 per stream: ring[G][3][B]
+    static constexpr int kStageStride = 2 * B + 4;   // float per stream and stage buffer: stage[2][G][2][B]
+    static constexpr size_t kRingOff = kZOff + sizeof(float2) * G * 2 * NP;
+    static constexpr size_t kStageOff = kRingOff + sizeof(float2) * G * kRingStride;
+    static constexpr size_t kBytes = kStageOff + sizeof(float) * 2 * G * kStageStride;
+    static constexpr bool kFits = kBytes <= 227 * 1024 && kThreads <= 1024;
+    // Register budget.  Warps are allocated in groups of four; as many CTAs per SM as shared memory allows (up to
+    // four) while every thread keeps at least 80 registers.
+    static constexpr int kWarpsAlloc = (kThreads / 32 + 3) / 4 * 4;
     static constexpr int kBySmem = (int)((227 * 1024) / (kBytes + 1024));
-    static constexpr int kByRegs = 65536 / (80 * kThreads);
+    static constexpr int kByRegs = 65536 / (80 * 32 * kWarpsAlloc);
     static constexpr int kMinBlocks0 = kBySmem < kByRegs ? kBySmem : kByRegs;
     static constexpr int kMinBlocks = kMinBlocks0 < 1 ? 1 : (kMinBlocks0 > 4 ? 4 : kMinBlocks0);
+    static constexpr int kMaxRegs0 = (65536 / (kMinBlocks * 32 * kWarpsAlloc)) / 8 * 8;
+    static constexpr int kMaxRegs = kMaxRegs0 > 168 ? 168 : (kMaxRegs0 < 32 ? 32 : kMaxRegs0);
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 // EQ warp
 // ---------------------------------------------------------------------------------------------------------------
-// One DF2T step for the stereo pair, reference operation order (biquad 0.4.2 DirectForm2Transposed::run behind
+// One DF2T step, reference operation order (biquad 0.4.2 DirectForm2Transposed::run behind
 // src/dsp/parametric_eq.rs:116-122):   out = s1 + b0*x;  s1 = (s2 + b1*x) - a1*out;  s2 = b2*x - a2*out
-// Every product and every sum is rounded separately: x*c via FMUL2, sums via FFMA2(m, 1.0, s) == round(m + s).
-__device__ __forceinline__ float2 df2t_step(float2 x, float2& s1, float2& s2, float2 b0, float2 b1, float2 b2, float2 na1,
-                                            float2 na2, float2 one) {
-    const float2 m0 = __fmul2_rn(b0, x);
-    const float2 out = __ffma2_rn(m0, one, s1);
-    const float2 m1 = __fmul2_rn(b1, x);
-    const float2 t = __ffma2_rn(m1, one, s2);
-    const float2 m2 = __fmul2_rn(na1, out);
-    s1 = __ffma2_rn(m2, one, t);
-    const float2 m3 = __fmul2_rn(b2, x);
-    const float2 m4 = __fmul2_rn(na2, out);
-    s2 = __ffma2_rn(m4, one, m3);
+// Explicit round-to-nearest intrinsics: every product and sum is rounded separately and is never contracted into an
+// FMA (Rust does not contract; the cascade's output moves by 3.8e-4 if it is).  Left and right are two independent
+// scalar chains in the same lane, which gives the in-order warp the instruction-level parallelism to cover the
+// 4-cycle FP32 latency.  (The packed f32x2 form has half the instructions but one chain; measured slower, and ptxas
+// 12.9 contracts mul.f32x2 + add.f32x2 into FFMA2 even under -fmad=false.)
+__device__ __forceinline__ float df2t_step(float x, float& s1, float& s2, float b0, float b1, float b2, float a1, float a2) {
+    const float out = __fadd_rn(s1, __fmul_rn(b0, x));
+    s1 = __fsub_rn(__fadd_rn(s2, __fmul_rn(b1, x)), __fmul_rn(a1, out));
+    s2 = __fsub_rn(__fmul_rn(b2, x), __fmul_rn(a2, out));
     return out;
 }
 
-// One engine block through the band-systolic chain of one warp.  Lane (g, j) filters sample n = step - D*j with band
-// j; step runs 0 .. nb-1+9D.  The steady state (every lane busy) is branch-free and unrolled by four; the fill and
-// drain steps (and ragged or partly disabled cases) go through the checked step, which commits state by select.
-// FAST: nb == B and no valid lane is disabled.
-template <int B, bool FAST>
-__device__ __forceinline__ void eq_block_systolic(const float* __restrict__ xl, const float* __restrict__ xr, float2* __restrict__ dst,
-                                                  int nb, int j, int src_lane, bool lane_valid, bool en, float2& s1, float2& s2,
-                                                  float2 b0, float2 b1, float2 b2, float2 na1, float2 na2, float2 one) {
-    static_assert(kEqSkew == 2, "register rotation below is written for a skew of two");
-    [[maybe_unused]] constexpr int D = kEqSkew;
-    constexpr int kLag = (kEqGroup - 1) * D;          // steps until the last band sees sample 0
-    constexpr int kHead = (kLag + 3) / 4 * 4;         // checked steps before the unrolled steady state
-    const bool first = (j == 0), last = (j == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
-    float2 o0 = make_float2(0.f, 0.f), o1 = o0;       // this lane's outputs of the previous two steps (o1 older)
-
-    auto checked_step = [&](int step) {
-        const int n = step - D * j;
-        const bool act = lane_valid && n >= 0 && n < nb;
-        float2 x;
-        x.x = __shfl_sync(0xffffffffu, o1.x, src_lane);
-        x.y = __shfl_sync(0xffffffffu, o1.y, src_lane);
-        const int nc = step < B ? step : B - 1;
-        const float il = xl[nc], ir = xr[nc];
-        x.x = first ? il : x.x;
-        x.y = first ? ir : x.y;
-        float2 t1 = s1, t2 = s2;
-        float2 out = df2t_step(x, t1, t2, b0, b1, b2, na1, na2, one);
-        const bool upd = act && en;
-        s1.x = upd ? t1.x : s1.x; s1.y = upd ? t1.y : s1.y;
-        s2.x = upd ? t2.x : s2.x; s2.y = upd ? t2.y : s2.y;
-        out.x = upd ? out.x : x.x; out.y = upd ? out.y : x.y;
-        if (act && last) dst[n] = out;
-        o1 = o0; o0 = out;
-    };
-
-    if constexpr (!FAST) {
-        for (int step = 0; step < nb + kLag; ++step) checked_step(step);
-    } else {
-#pragma unroll 1
-    for (int step = 0; step < kHead; ++step) checked_step(step);
-    // steady state: every lane holds a live sample; lanes of absent streams compute on garbage that is never stored
-    float2* dlast = dst - kLag;
-#pragma unroll 1
-    for (int step = kHead; step < B; step += 4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(xl + step);
-        const float4 r4 = *reinterpret_cast<const float4*>(xr + step);
-        const float il[4] = {l4.x, l4.y, l4.z, l4.w};
-        const float ir[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            float2 x;
-            x.x = __shfl_sync(0xffffffffu, o1.x, src_lane);
-            x.y = __shfl_sync(0xffffffffu, o1.y, src_lane);
-            x.x = first ? il[u] : x.x;
-            x.y = first ? ir[u] : x.y;
-            const float2 out = df2t_step(x, s1, s2, b0, b1, b2, na1, na2, one);
-            if (last) dlast[step + u] = out;
-            o1 = o0; o0 = out;
-        }
-    }
-#pragma unroll 1
-    for (int step = B; step < B + kLag; ++step) checked_step(step);
-    }
-}
-
+// EQ warp `w` of the CTA.  Lane (c, j): chain c = 3w + lane/10 is one (stream, channel) pair, j its band.
+// Band j runs D = 4 samples behind band j-1 and receives its input from the neighbouring lane by shuffle; the
+// shuffle of an output is issued the moment it exists and consumed four steps later, so its latency never stalls the
+// in-order warp.  Every band's recurrence is the strictly sequential reference recurrence.
 template <int N, int G>
-__device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned char* smem, int stream0) {
+__device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned char* smem, int stream0, int w) {
     using SM = RenderSmem<N, G>;
     constexpr int B = SM::B;
     constexpr int D = kEqSkew;
+    constexpr int kLag = (kEqGroup - 1) * D;  // steps the last band runs behind the first
+    static_assert(D == 4 && kLag % 4 == 0 && (B - kLag) % 4 == 0 && B >= kLag, "unroll-by-four layout of the systolic loop");
     constexpr int kCount = SM::kThreads;
-    float2* ring = reinterpret_cast<float2*>(smem + SM::kRingOff);
+    float* ring_f = reinterpret_cast<float*>(smem + SM::kRingOff);
     float* stage = reinterpret_cast<float*>(smem + SM::kStageOff);
 
-    const int lane = threadIdx.x;
-    const int g_raw = lane / kEqGroup;
-    const int j = lane - g_raw * kEqGroup;
-    const int g = g_raw < G ? g_raw : G - 1;
+    const int lane = threadIdx.x & 31;
+    const int c_raw = 3 * w + lane / kEqGroup;           // chain index in the CTA: 2*stream + channel
+    const int j = lane % kEqGroup;
+    const bool chain_ok = (lane < 3 * kEqGroup) && (c_raw < 2 * G);
+    const int c = chain_ok ? c_raw : 0;
+    const int g = c >> 1, ch = c & 1;
     const int s = stream0 + g;
-    const bool lane_valid = (g_raw < G) && (s < p.n_streams);
+    const bool lane_valid = chain_ok && (s < p.n_streams);
     const bool do_eq = p.eq_enable != 0;
 
-    float2 b0 = make_float2(0.f, 0.f), b1 = b0, b2 = b0, na1 = b0, na2 = b0, s1 = b0, s2 = b0;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f, s1 = 0.f, s2 = 0.f;
     bool en = false;
-    const float2 one = make_float2(p.one, p.one);
     if (lane_valid && do_eq && j < p.n_bands) {
-        const float* c = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + j) * kEqCoefStride;
-        b0 = make_float2(c[0], c[0]); b1 = make_float2(c[1], c[1]); b2 = make_float2(c[2], c[2]);
-        na1 = make_float2(-c[3], -c[3]); na2 = make_float2(-c[4], -c[4]);
-        en = c[5] != 0.f;
-        const float4 st = p.eqs[(size_t)s * kMaxBands + j];
-        s1 = make_float2(st.x, st.y); s2 = make_float2(st.z, st.w);
+        const float* cf = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + j) * kEqCoefStride;
+        b0 = cf[0]; b1 = cf[1]; b2 = cf[2]; a1 = cf[3]; a2 = cf[4];
+        en = cf[5] != 0.f;
+        const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + j);
+        s1 = st[ch]; s2 = st[2 + ch];
     }
 
-    // stage loader: rows (g', c) of block t -> stage[t&1][g'][c][0..B)
+    // stage loader (EQ warp 0 only): rows (g', c') of block t -> stage[t&1][g'][c'][0..B)
     auto issue_stage = [&](int t) {
         constexpr int kChunksPerRow = B / 4;
         constexpr int kChunks = G * 2 * kChunksPerRow;
-        float* dst_base = stage + (size_t)(t & 1) * G * 2 * B;
+        float* dst_base = stage + (size_t)(t & 1) * G * SM::kStageStride;
         const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
         if (nb == B) {
-            for (int q = lane; q < kChunks; q += 32) {
+            for (int q = threadIdx.x; q < kChunks; q += SM::kEqThreads) {
                 const int row = q / kChunksPerRow, off = q - row * kChunksPerRow;
                 const int sg = stream0 + (row >> 1);
                 if (sg < p.n_streams) {
                     const float* src = p.in + ((size_t)sg * 2 + (row & 1)) * p.row_stride + (size_t)t * B + off * 4;
-                    cp_async16(dst_base + row * B + off * 4, src);
+                    cp_async16(dst_base + (row >> 1) * SM::kStageStride + (row & 1) * B + off * 4, src);
                 }
             }
         } else {
             // ragged last block (EQ-only mode, any host-buffer length): plain guarded loads
-            for (int q = lane; q < G * 2 * B; q += 32) {
+            for (int q = threadIdx.x; q < G * 2 * B; q += SM::kEqThreads) {
                 const int row = q / B, n = q - row * B;
                 const int sg = stream0 + (row >> 1);
                 if (sg < p.n_streams && n < nb)
-                    dst_base[row * B + n] = p.in[((size_t)sg * 2 + (row & 1)) * p.row_stride + (size_t)t * B + n];
+                    dst_base[(row >> 1) * SM::kStageStride + (row & 1) * B + n] =
+                        p.in[((size_t)sg * 2 + (row & 1)) * p.row_stride + (size_t)t * B + n];
             }
         }
         cp_async_commit();
     };
+    // All EQ warps cooperate on the loads.  Block t's rows are complete once every EQ warp has waited for its own
+    // copies and the EQ warps have met at their barrier; the same barrier proves that every EQ warp is done reading
+    // the other stage buffer (block t-1), so the copies of block t+1 may start overwriting it.
+    auto wait_stage = [&](int t) {
+        cp_async_wait<0>();
+        if (SM::kEqWarps > 1) bar_sync(kBarEq, SM::kEqThreads); else __syncwarp();
+        if (t + 1 < p.n_blocks) issue_stage(t + 1);
+    };
 
     const int src_lane = (j == 0) ? lane : lane - 1;
-    // every valid lane filters (no disabled band in this warp): the steady-state loop needs no per-lane selects
-    const bool all_fast = __all_sync(0xffffffffu, en || !lane_valid);
-    issue_stage(0);
-    for (int t = 0; t < p.n_blocks; ++t) {
-        if (t + 1 < p.n_blocks) { issue_stage(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-        __syncwarp();
-        if (t >= 2) bar_sync(kBarEmpty0 + (t & 1), kCount);  // ring slot t%3 was last read as history of block t-2
-        const int slot = t % 3;
-        const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
-        const float* st_base = stage + (size_t)(t & 1) * G * 2 * B;
-        if (!do_eq) {
-            // EQ off (src/lib.rs:1179): the warp only interleaves left/right into the ring
-            for (int q = lane; q < G * B; q += 32) {
-                const int gg = q / B, n = q - gg * B;
-                ring[(gg * 3 + slot) * B + n] = make_float2(st_base[(gg * 2) * B + n], st_base[(gg * 2 + 1) * B + n]);
-            }
-        } else {
-            const float* xl = st_base + (g * 2) * B;
-            const float* xr = xl + B;
-            float2* dst = ring + (g * 3 + slot) * B;
-            if (nb == B && all_fast) eq_block_systolic<B, true>(xl, xr, dst, B, j, src_lane, lane_valid, en, s1, s2, b0, b1, b2, na1, na2, one);
-            else eq_block_systolic<B, false>(xl, xr, dst, nb, j, src_lane, lane_valid, en, s1, s2, b0, b1, b2, na1, na2, one);
+    const bool first = (j == 0), last = (j == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
+    float xs[4] = {0.f, 0.f, 0.f, 0.f};  // inputs of this lane's next four steps, already shuffled over from lane-1
+
+    // four steady-state steps: every lane holds a live sample (lanes of absent streams run on garbage, never stored)
+    auto fast4 = [&](float4 in, float* dstp) {
+        const float iv[4] = {in.x, in.y, in.z, in.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float x = first ? iv[u] : xs[u];
+            const float y = df2t_step(x, s1, s2, b0, b1, b2, a1, a2);
+            if (last) dstp[2 * u] = y;
+            xs[u] = __shfl_sync(0xffffffffu, y, src_lane);
         }
-        __threadfence_block();
-        bar_arrive(kBarFull0 + (t & 1), kCount);
+    };
+    // four checked steps (pipeline fill and drain, ragged blocks, disabled bands): state and output are committed only
+    // where `act`; a disabled band passes its input through untouched and keeps its state (parametric_eq.rs:118-120).
+    // n0 = this lane's sample index at the first of the four steps, valid samples are [0, nb).
+    auto checked4 = [&](float4 in, int n0, int nb, float* dst0) {
+        const float iv[4] = {in.x, in.y, in.z, in.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int n = n0 + u;
+            const bool act = lane_valid && n >= 0 && n < nb;
+            const float x = first ? iv[u] : xs[u];
+            float t1 = s1, t2 = s2;
+            float y = df2t_step(x, t1, t2, b0, b1, b2, a1, a2);
+            const bool upd = act && en;
+            s1 = upd ? t1 : s1; s2 = upd ? t2 : s2;
+            y = upd ? y : x;
+            if (act && last) dst0[2 * n] = y;
+            xs[u] = __shfl_sync(0xffffffffu, y, src_lane);
+        }
+    };
+    auto ld4 = [&](const float* row, int i) { return *reinterpret_cast<const float4*>(row + i); };
+
+    // every valid lane filters and the launch is whole blocks: the chain runs continuously across the launch's blocks,
+    // filling once at the start and draining once at the end
+    const bool all_fast = __all_sync(0xffffffffu, en || !lane_valid);
+    const bool continuous = do_eq && p.tail_frames == B && (SM::kEqWarps > 1 ? __syncthreads_and_eq<SM::kEqThreads>(all_fast) : all_fast);
+    float* ring_c = ring_f + ((size_t)g * SM::kRingStride) * 2 + ch;  // this chain's channel inside the float2 ring
+    issue_stage(0);
+    if (continuous) {
+        for (int t = 0; t < p.n_blocks; ++t) {
+            wait_stage(t);
+            const float* row = stage + ((size_t)(t & 1) * G + g) * SM::kStageStride + ch * B;
+            // part A: the first band starts block t while the last band finishes block t-1
+            if (t == 0) {
+#pragma unroll 1
+                for (int i = 0; i < kLag; i += 4) checked4(ld4(row, i), i - D * j, B, ring_c);
+            } else {
+                float* dprev = ring_c + (((t - 1) % 3) * B + (B - kLag)) * 2;
+#pragma unroll 1
+                for (int i = 0; i < kLag; i += 4) fast4(ld4(row, i), dprev + 2 * i);
+                __threadfence_block();
+                bar_arrive(kBarFull0 + ((t - 1) & 1), kCount);
+            }
+            if (t >= 2) bar_sync(kBarEmpty0 + (t & 1), kCount);  // ring slot t%3 was last read as history of block t-2
+            // part B: the last band writes the head of block t
+            float* dcur = ring_c + ((t % 3) * B) * 2;
+#pragma unroll 1
+            for (int i = kLag; i < B; i += 4) fast4(ld4(row, i), dcur + 2 * (i - kLag));
+        }
+        {
+            // drain: the first band has no more input; band j still owes its last D*j samples
+            float* dl = ring_c + (((p.n_blocks - 1) % 3) * B) * 2;
+#pragma unroll 1
+            for (int i = 0; i < kLag; i += 4) checked4(make_float4(0.f, 0.f, 0.f, 0.f), B + i - D * j, B, dl);
+            __threadfence_block();
+            bar_arrive(kBarFull0 + ((p.n_blocks - 1) & 1), kCount);
+        }
+    } else {
+        for (int t = 0; t < p.n_blocks; ++t) {
+            wait_stage(t);
+            if (t >= 2) bar_sync(kBarEmpty0 + (t & 1), kCount);
+            const int slot = t % 3;
+            const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
+            const float* st_base = stage + (size_t)(t & 1) * G * SM::kStageStride;
+            if (!do_eq) {
+                // EQ off (src/lib.rs:1179): the EQ warps only interleave left/right into the ring
+                float2* ring = reinterpret_cast<float2*>(ring_f);
+                for (int q = threadIdx.x; q < G * B; q += SM::kEqThreads) {
+                    const int gg = q / B, n = q - gg * B;
+                    ring[gg * SM::kRingStride + slot * B + n] =
+                        make_float2(st_base[gg * SM::kStageStride + n], st_base[gg * SM::kStageStride + B + n]);
+                }
+            } else {
+                // per-block chain (ragged last block and/or disabled bands): fill, run and drain inside the block
+                const float* row = st_base + g * SM::kStageStride + ch * B;
+                float* dst = ring_c + (slot * B) * 2;
+                xs[0] = xs[1] = xs[2] = xs[3] = 0.f;
+#pragma unroll 1
+                for (int i = 0; i < nb + kLag; i += 4) {
+                    const float4 in = (i < B) ? ld4(row, i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    checked4(in, i - D * j, nb, dst);
+                }
+            }
+            __threadfence_block();
+            bar_arrive(kBarFull0 + (t & 1), kCount);
+        }
     }
-    if (lane_valid && do_eq && j < p.n_bands) p.eqs[(size_t)s * kMaxBands + j] = make_float4(s1.x, s1.y, s2.x, s2.y);
+    if (lane_valid && do_eq && j < p.n_bands) {
+        float* st = reinterpret_cast<float*>(p.eqs + (size_t)s * kMaxBands + j);
+        st[ch] = s1; st[2 + ch] = s2;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -401,7 +466,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     const float2* tw = reinterpret_cast<const float2*>(smem + SM::kTwOff);
     float2* ring = reinterpret_cast<float2*>(smem + SM::kRingOff);
 
-    const int ft = threadIdx.x - 32;
+    const int ft = threadIdx.x - SM::kEqThreads;
     const int g = ft / T, tid = ft - g * T;
     const int s = stream0 + g;
     const bool valid = s < p.n_streams;
@@ -409,7 +474,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     float2* b1 = b0 + NP;
     float2* zbuf = Pl::kOutInB0 ? b0 : b1;   // forward transform lands here
     float2* wbuf = Pl::kOutInB0 ? b1 : b0;   // frequency-domain product goes here
-    float2* ring_g = ring + (size_t)g * 3 * B;
+    float2* ring_g = ring + (size_t)g * SM::kRingStride;
 
     int nparts = 1;
     const float4* filt = p.filt;
@@ -511,7 +576,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
 }
 
 template <int N, int G>
-__global__ void __launch_bounds__(RenderSmem<N, G>::kThreads, RenderSmem<N, G>::kMinBlocks) render_kernel(const RenderParams p) {
+__global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const RenderParams p) {
     using SM = RenderSmem<N, G>;
     extern __shared__ __align__(16) unsigned char smem[];
     const int stream0 = blockIdx.x * G;
@@ -523,11 +588,11 @@ __global__ void __launch_bounds__(RenderSmem<N, G>::kThreads, RenderSmem<N, G>::
         for (int q = threadIdx.x; q < G * SM::B; q += SM::kThreads) {
             const int g = q / SM::B, n = q - g * SM::B;
             const int s = stream0 + g;
-            ring[(g * 3 + 2) * SM::B + n] = (s < p.n_streams) ? p.prev[(size_t)s * SM::B + n] : make_float2(0.f, 0.f);
+            ring[g * SM::kRingStride + 2 * SM::B + n] = (s < p.n_streams) ? p.prev[(size_t)s * SM::B + n] : make_float2(0.f, 0.f);
         }
     }
     __syncthreads();
-    if (threadIdx.x < 32) eq_warp_main<N, G>(p, smem, stream0);
+    if (threadIdx.x < SM::kEqThreads) eq_warp_main<N, G>(p, smem, stream0, threadIdx.x >> 5);
     else conv_warps_main<N, G>(p, smem, stream0);
 }
 
