@@ -234,10 +234,10 @@ template <int N, int G> struct RenderSmem {
     static constexpr size_t kTwOff = 0;                                      // float2 tw[N]
     static constexpr size_t kZOff = kTwOff + sizeof(float2) * N;             // float2 z[G][2][NP]
     // per-stream strides carry a 16-byte pad so that neighbouring streams sit on different banks
-    static constexpr int kRingStride = 3 * B + 2;    // float2 per stream: ring[G][3][B]
+    static constexpr int kRingStride = 6 * B + 4;    // float per stream: planar ring[G][3 slots][2 channels][B]
     static constexpr int kStageStride = 2 * B + 4;   // float per stream and stage buffer: stage[2][G][2][B]
     static constexpr size_t kRingOff = kZOff + sizeof(float2) * G * 2 * NP;
-    static constexpr size_t kStageOff = kRingOff + sizeof(float2) * G * kRingStride;
+    static constexpr size_t kStageOff = kRingOff + sizeof(float) * G * kRingStride;
     static constexpr size_t kBytes = kStageOff + sizeof(float) * 2 * G * kStageStride;
     static constexpr bool kFits = kBytes <= 227 * 1024 && kThreads <= 1024;
     // Register budget.  Warps are allocated in groups of four; as many CTAs per SM as shared memory allows (up to
@@ -343,16 +343,18 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     const bool first = (j == 0), last = (j == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
     float xs[4] = {0.f, 0.f, 0.f, 0.f};  // inputs of this lane's next four steps, already shuffled over from lane-1
 
-    // four steady-state steps: every lane holds a live sample (lanes of absent streams run on garbage, never stored)
+    // four steady-state steps: every lane holds a live sample (lanes of absent streams run on garbage, never stored);
+    // the last band stores its four outputs with one 16-byte store
     auto fast4 = [&](float4 in, float* dstp) {
         const float iv[4] = {in.x, in.y, in.z, in.w};
+        float y[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const float x = first ? iv[u] : xs[u];
-            const float y = df2t_step(x, s1, s2, b0, b1, b2, a1, a2);
-            if (last) dstp[2 * u] = y;
-            xs[u] = __shfl_sync(0xffffffffu, y, src_lane);
+            y[u] = df2t_step(x, s1, s2, b0, b1, b2, a1, a2);
+            xs[u] = __shfl_sync(0xffffffffu, y[u], src_lane);
         }
+        if (last) *reinterpret_cast<float4*>(dstp) = make_float4(y[0], y[1], y[2], y[3]);
     };
     // four checked steps (pipeline fill and drain, ragged blocks, disabled bands): state and output are committed only
     // where `act`; a disabled band passes its input through untouched and keeps its state (parametric_eq.rs:118-120).
@@ -369,17 +371,28 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             const bool upd = act && en;
             s1 = upd ? t1 : s1; s2 = upd ? t2 : s2;
             y = upd ? y : x;
-            if (act && last) dst0[2 * n] = y;
+            if (act && last) dst0[n] = y;
             xs[u] = __shfl_sync(0xffffffffu, y, src_lane);
         }
     };
     auto ld4 = [&](const float* row, int i) { return *reinterpret_cast<const float4*>(row + i); };
+    // steady-state steps [i0, i1) of the current block; the input of the next four steps is loaded one iteration ahead
+    auto fast_run = [&](const float* row, int i0, int i1, float* dst_at_i0) {
+        float4 cur = ld4(row, i0);
+#pragma unroll 1
+        for (int i = i0; i < i1; i += 4) {
+            const int inext = (i + 4 < B) ? i + 4 : i;
+            const float4 nxt = ld4(row, inext);
+            fast4(cur, dst_at_i0 + (i - i0));
+            cur = nxt;
+        }
+    };
 
     // every valid lane filters and the launch is whole blocks: the chain runs continuously across the launch's blocks,
     // filling once at the start and draining once at the end
     const bool all_fast = __all_sync(0xffffffffu, en || !lane_valid);
     const bool continuous = do_eq && p.tail_frames == B && (SM::kEqWarps > 1 ? __syncthreads_and_eq<SM::kEqThreads>(all_fast) : all_fast);
-    float* ring_c = ring_f + ((size_t)g * SM::kRingStride) * 2 + ch;  // this chain's channel inside the float2 ring
+    float* ring_c = ring_f + (size_t)g * SM::kRingStride + ch * B;  // this chain's channel row of slot 0 (slots are 2*B apart)
     issue_stage(0);
     if (continuous) {
         for (int t = 0; t < p.n_blocks; ++t) {
@@ -388,23 +401,20 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             // part A: the first band starts block t while the last band finishes block t-1
             if (t == 0) {
 #pragma unroll 1
-                for (int i = 0; i < kLag; i += 4) checked4(ld4(row, i), i - D * j, B, ring_c);
+                for (int i = 0; i < kLag; i += 4) checked4(ld4(row, i), i - D * j, B, ring_c);  // (the last band stores nothing yet)
             } else {
-                float* dprev = ring_c + (((t - 1) % 3) * B + (B - kLag)) * 2;
-#pragma unroll 1
-                for (int i = 0; i < kLag; i += 4) fast4(ld4(row, i), dprev + 2 * i);
+                float* dprev = ring_c + ((t - 1) % 3) * 2 * B + (B - kLag);
+                fast_run(row, 0, kLag, dprev);
                 __threadfence_block();
                 bar_arrive(kBarFull0 + ((t - 1) & 1), kCount);
             }
             if (t >= 2) bar_sync(kBarEmpty0 + (t & 1), kCount);  // ring slot t%3 was last read as history of block t-2
             // part B: the last band writes the head of block t
-            float* dcur = ring_c + ((t % 3) * B) * 2;
-#pragma unroll 1
-            for (int i = kLag; i < B; i += 4) fast4(ld4(row, i), dcur + 2 * (i - kLag));
+            fast_run(row, kLag, B, ring_c + (t % 3) * 2 * B);
         }
         {
             // drain: the first band has no more input; band j still owes its last D*j samples
-            float* dl = ring_c + (((p.n_blocks - 1) % 3) * B) * 2;
+            float* dl = ring_c + ((p.n_blocks - 1) % 3) * 2 * B;
 #pragma unroll 1
             for (int i = 0; i < kLag; i += 4) checked4(make_float4(0.f, 0.f, 0.f, 0.f), B + i - D * j, B, dl);
             __threadfence_block();
@@ -419,16 +429,14 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             const float* st_base = stage + (size_t)(t & 1) * G * SM::kStageStride;
             if (!do_eq) {
                 // EQ off (src/lib.rs:1179): the EQ warps only interleave left/right into the ring
-                float2* ring = reinterpret_cast<float2*>(ring_f);
-                for (int q = threadIdx.x; q < G * B; q += SM::kEqThreads) {
-                    const int gg = q / B, n = q - gg * B;
-                    ring[gg * SM::kRingStride + slot * B + n] =
-                        make_float2(st_base[gg * SM::kStageStride + n], st_base[gg * SM::kStageStride + B + n]);
+                for (int q = threadIdx.x; q < G * 2 * B; q += SM::kEqThreads) {
+                    const int gg = q / (2 * B), n = q - gg * 2 * B;  // n runs over [left row | right row]
+                    ring_f[gg * SM::kRingStride + slot * 2 * B + n] = st_base[gg * SM::kStageStride + n];
                 }
             } else {
                 // per-block chain (ragged last block and/or disabled bands): fill, run and drain inside the block
                 const float* row = st_base + g * SM::kStageStride + ch * B;
-                float* dst = ring_c + (slot * B) * 2;
+                float* dst = ring_c + slot * 2 * B;
                 xs[0] = xs[1] = xs[2] = xs[3] = 0.f;
 #pragma unroll 1
                 for (int i = 0; i < nb + kLag; i += 4) {
@@ -464,7 +472,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     constexpr int kCount = SM::kThreads;
     using Pl = FftPlan<N, T>;
     const float2* tw = reinterpret_cast<const float2*>(smem + SM::kTwOff);
-    float2* ring = reinterpret_cast<float2*>(smem + SM::kRingOff);
+    float* ring = reinterpret_cast<float*>(smem + SM::kRingOff);
 
     const int ft = threadIdx.x - SM::kEqThreads;
     const int g = ft / T, tid = ft - g * T;
@@ -474,7 +482,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     float2* b1 = b0 + NP;
     float2* zbuf = Pl::kOutInB0 ? b0 : b1;   // forward transform lands here
     float2* wbuf = Pl::kOutInB0 ? b1 : b0;   // frequency-domain product goes here
-    float2* ring_g = ring + (size_t)g * SM::kRingStride;
+    float* ring_g = ring + (size_t)g * SM::kRingStride;  // planar: slot k = [left row | right row] at k*2*B
 
     int nparts = 1;
     const float4* filt = p.filt;
@@ -494,8 +502,8 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     for (int t = 0; t < p.n_blocks; ++t) {
         bar_sync(kBarFull0 + (t & 1), kCount);
         const int cur = t % 3, prv = (t + 2) % 3;
-        const float2* xc = ring_g + cur * B;
-        const float2* xp = ring_g + prv * B;
+        const float* xc = ring_g + cur * 2 * B;
+        const float* xp = ring_g + prv * 2 * B;
         const bool release = (t + 2 < p.n_blocks);
         if (!valid) {
             if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount);
@@ -505,16 +513,15 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
             // EQ + gain only (StereoParametricEQ::process_block followed by the gain loop)
             const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
             for (int n = tid; n < nb; n += T) {
-                const float2 v = xc[n];
-                out_l[(size_t)t * B + n] = v.x * gain;
-                out_r[(size_t)t * B + n] = v.y * gain;
+                out_l[(size_t)t * B + n] = xc[n] * gain;
+                out_r[(size_t)t * B + n] = xc[B + n] * gain;
             }
             if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount);
             continue;
         }
         // ---- forward FFT of the overlap-save window [previous block | current block], z = left + i*right
         fft_run<N, T>(
-            tid, tw, b0, b1, [&](int i) { return i < B ? xp[i] : xc[i - B]; },
+            tid, tw, b0, b1, [&](int i) { return i < B ? make_float2(xp[i], xp[B + i]) : make_float2(xc[i - B], xc[i]); },
             [&](int i, float2 v) { zbuf[padi(i)] = v; }, stream_sync,
             [&]() { if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount); });
         stream_sync();
@@ -570,8 +577,8 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     }
     // overlap-save history for the next launch: the last filtered block
     if (valid && p.conv_enable && p.n_blocks > 0) {
-        const float2* xc = ring_g + ((p.n_blocks - 1) % 3) * B;
-        for (int n = tid; n < B; n += T) p.prev[(size_t)s * B + n] = xc[n];
+        const float* xc = ring_g + ((p.n_blocks - 1) % 3) * 2 * B;
+        for (int n = tid; n < B; n += T) p.prev[(size_t)s * B + n] = make_float2(xc[n], xc[B + n]);
     }
 }
 
@@ -584,11 +591,13 @@ __global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const Re
         float2* tw = reinterpret_cast<float2*>(smem + SM::kTwOff);
         for (int i = threadIdx.x; i < N; i += SM::kThreads) tw[i] = p.tw[i];
         // overlap-save history -> ring slot 2 (the "previous" slot of block 0)
-        float2* ring = reinterpret_cast<float2*>(smem + SM::kRingOff);
+        float* ring = reinterpret_cast<float*>(smem + SM::kRingOff);
         for (int q = threadIdx.x; q < G * SM::B; q += SM::kThreads) {
             const int g = q / SM::B, n = q - g * SM::B;
             const int s = stream0 + g;
-            ring[g * SM::kRingStride + 2 * SM::B + n] = (s < p.n_streams) ? p.prev[(size_t)s * SM::B + n] : make_float2(0.f, 0.f);
+            const float2 v = (s < p.n_streams) ? p.prev[(size_t)s * SM::B + n] : make_float2(0.f, 0.f);
+            ring[g * SM::kRingStride + 2 * 2 * SM::B + n] = v.x;
+            ring[g * SM::kRingStride + 2 * 2 * SM::B + SM::B + n] = v.y;
         }
     }
     __syncthreads();
