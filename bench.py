@@ -186,11 +186,6 @@ def run_reference(args, pkg):
 # --------------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------
-class _DevMem:
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-
 def run_gpu(args, pkg):
     import torch
     import torch.distributed as dist
@@ -223,13 +218,7 @@ def run_gpu(args, pkg):
         eng.sync()
     if world > 1:
         # one HRIR spectra table for the whole job: rank 0 transforms the IRs, NCCL broadcasts the spectra
-        ptr, nbytes = eng.filter_table()
-        table = torch.as_tensor(_DevMem(ptr, nbytes), device="cuda")
-        torch.cuda.synchronize()
-        dist.broadcast(table, src=0)
-        torch.cuda.synchronize()
-        if rank != 0:
-            eng.mark_filters_external(0, 1)
+        pkg.parallel.broadcast_filters(eng, src=0, partitions=1)
     for b in range(10):
         eng.eq_set_band(b, coeffs[b], True)
     eng.set_eq_enable(True)

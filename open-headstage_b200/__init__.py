@@ -5,8 +5,8 @@ The compute path is the hand-written CUDA in csrc/ behind the C ABI of include/o
 by _build.build_library()).  This package is the thin host side: a ctypes binding, Python mirrors of the
 reference's `ConvolutionEngine` / `StereoParametricEQ`, and the seeded synthetic inputs of the BASELINE configs.
 """
-from . import signals  # noqa: F401
-from ._build import build_library  # noqa: F401
+from . import parallel, signals  # noqa: F401
+from ._build import build_host_tests, build_library  # noqa: F401
 from .engine import (  # noqa: F401
     ALLPASS, BANDPASS, HIGHPASS, HIGHSHELF, LOWPASS, LOWSHELF, LSL, LSR, NOTCH, OHS_ALL, PEAK, RSL, RSR, SYMBOLS,
     BandConfig, ConvolutionEngine, Engine, OhsError, PinnedBuffer, StereoParametricEQ, eq_design, load_library,

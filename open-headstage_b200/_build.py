@@ -44,3 +44,17 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if r.returncode:
             raise RuntimeError("nvcc failed building libohs_cuda.so")
     return LIB
+
+
+HOST_TEST_BIN = os.path.join(HERE, "host", "ref_unit_tests")
+
+
+def build_host_tests(force: bool = False) -> str:
+    """g++ build of the C++ mirror's replay of the reference's unit tests (links libohs_cuda.so by rpath)."""
+    src = os.path.join(HERE, "host", "ref_unit_tests.cpp")
+    deps = [src, os.path.join(HERE, "host", "dsp.hpp"), os.path.join(ROOT, "include", "ohs.h")]
+    if force or not os.path.exists(HOST_TEST_BIN) or any(os.path.getmtime(d) > os.path.getmtime(HOST_TEST_BIN) for d in deps):
+        build_library()
+        cmd = ["g++", "-O2", "-std=c++17", "-o", HOST_TEST_BIN, src, "-L" + HERE, "-lohs_cuda", "-Wl,-rpath,$ORIGIN/.."]
+        subprocess.check_call(cmd, cwd=ROOT)
+    return HOST_TEST_BIN

@@ -30,7 +30,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert lib.ohs_abi_version() == 1
 
 
-def test_library_is_sm100a_and_uses_packed_fp32():
+def test_library_is_sm100a_native_code():
     import shutil
     import subprocess
 
@@ -41,9 +41,9 @@ def test_library_is_sm100a_and_uses_packed_fp32():
     elf = subprocess.run([cuobjdump, "-lelf", lib_path], capture_output=True, text=True).stdout
     assert "sm_100a" in elf
     sass = subprocess.run([cuobjdump, "-sass", lib_path], capture_output=True, text=True).stdout
-    # the EQ runs on the packed FP32 pipe: FMUL2 for the five products, FFMA2 (by an opaque 1.0) for the four sums
-    assert "FMUL2" in sass and "FFMA2" in sass
-    assert "LDGSTS" in sass  # cp.async input staging
+    assert "LDGSTS" in sass    # cp.async input staging into shared memory
+    assert "SHFL.IDX" in sass  # the band-systolic EQ chain
+    assert "BAR.ARV" in sass or "BAR.ARRIVE" in sass or "BAR.SYNC" in sass  # named-barrier producer/consumer hand-off
 
 
 @pytest.mark.parametrize("t", range(8))

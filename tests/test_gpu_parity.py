@@ -416,3 +416,14 @@ def test_full_size_config2_properties():
     yb = lin.process(x[::-1].copy()); lin.conv_reset()
     yab = lin.process(x + x[::-1])
     assert np.max(np.abs(ya + yb - yab)) <= TOL
+
+
+def test_cpp_mirror_replays_reference_unit_tests():
+    """open-headstage_b200/host/dsp.hpp: the C++ host mirror (reference type and method names over the C ABI) runs the
+    reference's five unit tests (ref_unit_tests.cpp) on the GPU."""
+    import subprocess
+
+    binary = ohs.build_host_tests()
+    r = subprocess.run([binary], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "PASSED" in r.stdout and "FAIL" not in r.stdout
