@@ -30,9 +30,9 @@
 namespace ohs {
 
 constexpr int kMaxBands = 10;
-constexpr int kEqGroup = 10;   // lanes per stream in the EQ warp
-constexpr int kMaxG = 7;       // streams per CTA; their 2G channels x 10 bands are spread over ceil(2G/3) EQ warps
-constexpr int kEqSkew = 4;     // samples between neighbouring bands of the systolic chain (hides the 26-cycle SHFL)
+constexpr int kEqGroup = 5;    // lanes per (stream, channel) chain in an EQ warp: two bands per lane
+constexpr int kMaxG = 7;       // streams per CTA; their 2G chains of 5 lanes are spread over ceil(G/3) EQ warps
+constexpr int kEqSkew = 4;     // samples between neighbouring lanes of the systolic chain (hides the 26-cycle SHFL)
 constexpr int kEqCoefStride = 8;  // floats per (eq_set, band): b0 b1 b2 a1 a2 enabled pad pad
 
 enum NamedBarrier { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarEq = 5, kBarStream0 = 6 };
@@ -228,7 +228,7 @@ template <int N, int G> struct RenderSmem {
     static constexpr int B = N / 2;
     static constexpr int T = (N / 8 >= 32) ? N / 8 : 32;   // convolution threads per stream
     static constexpr int NP = padded_len(N);
-    static constexpr int kEqWarps = (2 * G + 2) / 3;         // three (stream, channel) chains of 10 lanes per EQ warp
+    static constexpr int kEqWarps = (G + 2) / 3;             // six (stream, channel) chains of 5 lanes per EQ warp
     static constexpr int kEqThreads = 32 * kEqWarps;
     static constexpr int kThreads = kEqThreads + G * T;
     static constexpr size_t kTwOff = 0;                                      // float2 tw[N]
@@ -268,42 +268,54 @@ __device__ __forceinline__ float df2t_step(float x, float& s1, float& s2, float 
     return out;
 }
 
-// EQ warp `w` of the CTA.  Lane (c, j): chain c = 3w + lane/10 is one (stream, channel) pair, j its band.
-// Band j runs D = 4 samples behind band j-1 and receives its input from the neighbouring lane by shuffle; the
-// shuffle of an output is issued the moment it exists and consumed four steps later, so its latency never stalls the
-// in-order warp.  Every band's recurrence is the strictly sequential reference recurrence.
+// EQ warp `w` of the CTA.  Lane (c, l): chain c = 6w + lane/5 is one (stream, channel) pair; the lane runs bands
+// A = 2l and B = 2l+1 of the 10-band cascade.  The chain is systolic in time:
+//     step s:  band A filters sample s - 4l      (input: lane l-1's band-B output of step s-3, by SHFL; lane 0: the input row)
+//              band B filters sample s - 4l - 1  (input: this lane's band-A output of step s-1)
+// so the last band (lane 4, B) runs 17 samples behind the first.  The shuffle of an output is issued the moment it
+// exists and consumed three steps later, so its 26-cycle latency never stalls the in-order warp, and the two bands of a
+// lane are two independent dependent-chains that cover each other's 4-cycle FP32 latency.  Every band's recurrence
+// is the strictly sequential reference recurrence (see df2t_step): bit-exact.
 template <int N, int G>
 __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned char* smem, int stream0, int w) {
     using SM = RenderSmem<N, G>;
     constexpr int B = SM::B;
-    constexpr int D = kEqSkew;
-    constexpr int kLag = (kEqGroup - 1) * D;  // steps the last band runs behind the first
-    static_assert(D == 4 && kLag % 4 == 0 && (B - kLag) % 4 == 0 && B >= kLag, "unroll-by-four layout of the systolic loop");
+    constexpr int kOutLag = 4 * (kEqGroup - 1) + 1;  // 17: steps the last band runs behind the first
+    constexpr int kLag = 20;                          // kOutLag rounded to whole 4-step iterations (16-byte stores)
+    static_assert(kEqSkew == 4 && kEqGroup == 5 && kOutLag == 17 && (B - kLag) % 4 == 0 && B >= 2 * kLag, "systolic loop layout");
     constexpr int kCount = SM::kThreads;
     float* ring_f = reinterpret_cast<float*>(smem + SM::kRingOff);
     float* stage = reinterpret_cast<float*>(smem + SM::kStageOff);
 
     const int lane = threadIdx.x & 31;
-    const int c_raw = 3 * w + lane / kEqGroup;           // chain index in the CTA: 2*stream + channel
-    const int j = lane % kEqGroup;
-    const bool chain_ok = (lane < 3 * kEqGroup) && (c_raw < 2 * G);
+    const int c_raw = 6 * w + lane / kEqGroup;           // chain index in the CTA: 2*stream + channel
+    const int l = lane % kEqGroup;
+    const bool chain_ok = (lane < 6 * kEqGroup) && (c_raw < 2 * G);
     const int c = chain_ok ? c_raw : 0;
     const int g = c >> 1, ch = c & 1;
     const int s = stream0 + g;
     const bool lane_valid = chain_ok && (s < p.n_streams);
     const bool do_eq = p.eq_enable != 0;
 
-    float b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f, s1 = 0.f, s2 = 0.f;
-    bool en = false;
-    if (lane_valid && do_eq && j < p.n_bands) {
-        const float* cf = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + j) * kEqCoefStride;
-        b0 = cf[0]; b1 = cf[1]; b2 = cf[2]; a1 = cf[3]; a2 = cf[4];
-        en = cf[5] != 0.f;
-        const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + j);
-        s1 = st[ch]; s2 = st[2 + ch];
+    // band A = 2l, band B = 2l+1
+    float ab0 = 0.f, ab1 = 0.f, ab2 = 0.f, aa1 = 0.f, aa2 = 0.f, as1 = 0.f, as2 = 0.f;
+    float bb0 = 0.f, bb1 = 0.f, bb2 = 0.f, ba1 = 0.f, ba2 = 0.f, bs1 = 0.f, bs2 = 0.f;
+    bool en_a = false, en_b = false;
+    const bool has_a = lane_valid && do_eq && (2 * l) < p.n_bands, has_b = lane_valid && do_eq && (2 * l + 1) < p.n_bands;
+    if (has_a) {
+        const float* cf = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + 2 * l) * kEqCoefStride;
+        ab0 = cf[0]; ab1 = cf[1]; ab2 = cf[2]; aa1 = cf[3]; aa2 = cf[4]; en_a = cf[5] != 0.f;
+        const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + 2 * l);
+        as1 = st[ch]; as2 = st[2 + ch];
+    }
+    if (has_b) {
+        const float* cf = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + 2 * l + 1) * kEqCoefStride;
+        bb0 = cf[0]; bb1 = cf[1]; bb2 = cf[2]; ba1 = cf[3]; ba2 = cf[4]; en_b = cf[5] != 0.f;
+        const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + 2 * l + 1);
+        bs1 = st[ch]; bs2 = st[2 + ch];
     }
 
-    // stage loader (EQ warp 0 only): rows (g', c') of block t -> stage[t&1][g'][c'][0..B)
+    // stage loader: rows (g', c') of block t -> stage[t&1][g'][c'][0..B), all EQ warps cooperating
     auto issue_stage = [&](int t) {
         constexpr int kChunksPerRow = B / 4;
         constexpr int kChunks = G * 2 * kChunksPerRow;
@@ -330,67 +342,81 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
         }
         cp_async_commit();
     };
-    // All EQ warps cooperate on the loads.  Block t's rows are complete once every EQ warp has waited for its own
-    // copies and the EQ warps have met at their barrier; the same barrier proves that every EQ warp is done reading
-    // the other stage buffer (block t-1), so the copies of block t+1 may start overwriting it.
+    // Block t's rows are complete once every EQ warp has waited for its own copies and the EQ warps have met at their
+    // barrier; the same barrier proves that every EQ warp is done reading the other stage buffer (block t-1), so the
+    // copies of block t+1 may start overwriting it.
     auto wait_stage = [&](int t) {
         cp_async_wait<0>();
         if (SM::kEqWarps > 1) bar_sync(kBarEq, SM::kEqThreads); else __syncwarp();
         if (t + 1 < p.n_blocks) issue_stage(t + 1);
     };
 
-    const int src_lane = (j == 0) ? lane : lane - 1;
-    const bool first = (j == 0), last = (j == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
-    float xs[4] = {0.f, 0.f, 0.f, 0.f};  // inputs of this lane's next four steps, already shuffled over from lane-1
+    const int src_lane = (l == 0) ? lane : lane - 1;
+    const bool first = (l == 0), last = (l == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
+    float xs[4] = {0.f, 0.f, 0.f, 0.f};   // band-A inputs of the next steps, shuffled over from lane l-1
+    float ya_prev = 0.f;                   // this lane's band-A output of the previous step
+    float yl[4] = {0.f, 0.f, 0.f, 0.f};   // band-B outputs of the last four steps (the last lane stores them in groups)
 
-    // four steady-state steps: every lane holds a live sample (lanes of absent streams run on garbage, never stored);
-    // the last band stores its four outputs with one 16-byte store
-    auto fast4 = [&](float4 in, float* dstp) {
-        const float iv[4] = {in.x, in.y, in.z, in.w};
-        float y[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float x = first ? iv[u] : xs[u];
-            y[u] = df2t_step(x, s1, s2, b0, b1, b2, a1, a2);
-            xs[u] = __shfl_sync(0xffffffffu, y[u], src_lane);
-        }
-        if (last) *reinterpret_cast<float4*>(dstp) = make_float4(y[0], y[1], y[2], y[3]);
-    };
-    // four checked steps (pipeline fill and drain, ragged blocks, disabled bands): state and output are committed only
-    // where `act`; a disabled band passes its input through untouched and keeps its state (parametric_eq.rs:118-120).
-    // n0 = this lane's sample index at the first of the four steps, valid samples are [0, nb).
-    auto checked4 = [&](float4 in, int n0, int nb, float* dst0) {
+    // Four steady-state steps (local steps i0 .. i0+3): every lane holds live samples (lanes of absent streams run on
+    // garbage that is never stored).  At the first of the four steps the last lane completes an aligned group of four
+    // output samples, [i0-20, i0-17] of the block being written, and stores it with one 16-byte store.
+    auto fast4 = [&](float4 in, float* dst_group) {
         const float iv[4] = {in.x, in.y, in.z, in.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int n = n0 + u;
-            const bool act = lane_valid && n >= 0 && n < nb;
-            const float x = first ? iv[u] : xs[u];
-            float t1 = s1, t2 = s2;
-            float y = df2t_step(x, t1, t2, b0, b1, b2, a1, a2);
-            const bool upd = act && en;
-            s1 = upd ? t1 : s1; s2 = upd ? t2 : s2;
-            y = upd ? y : x;
-            if (act && last) dst0[n] = y;
-            xs[u] = __shfl_sync(0xffffffffu, y, src_lane);
+            const float xa = first ? iv[u] : xs[u];
+            const float yb = df2t_step(ya_prev, bs1, bs2, bb0, bb1, bb2, ba1, ba2);
+            ya_prev = df2t_step(xa, as1, as2, ab0, ab1, ab2, aa1, aa2);
+            xs[(u + 3) & 3] = __shfl_sync(0xffffffffu, yb, src_lane);
+            if (u == 0 && last) *reinterpret_cast<float4*>(dst_group) = make_float4(yl[1], yl[2], yl[3], yb);
+            yl[u] = yb;
         }
     };
-    auto ld4 = [&](const float* row, int i) { return *reinterpret_cast<const float4*>(row + i); };
-    // steady-state steps [i0, i1) of the current block; the input of the next four steps is loaded one iteration ahead
+    // Four checked steps (pipeline fill and drain, ragged blocks, disabled bands): state and outputs are committed only
+    // where a band holds a live sample; a disabled band passes its input through and keeps its state
+    // (src/dsp/parametric_eq.rs:118-120).  na0 = band A's sample index at the first of the four steps; live samples
+    // are [0, nb); the last lane stores sample by sample into dst0[n].
+    auto checked4 = [&](float4 in, int na0, int nb, float* dst0) {
+        const float iv[4] = {in.x, in.y, in.z, in.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int na = na0 + u, nbi = na - 1;
+            const bool act_a = lane_valid && na >= 0 && na < nb, act_b = lane_valid && nbi >= 0 && nbi < nb;
+            const float xa = first ? iv[u] : xs[u];
+            float t1 = bs1, t2 = bs2;
+            float yb = df2t_step(ya_prev, t1, t2, bb0, bb1, bb2, ba1, ba2);
+            const bool upd_b = act_b && en_b;
+            bs1 = upd_b ? t1 : bs1; bs2 = upd_b ? t2 : bs2;
+            yb = upd_b ? yb : ya_prev;
+            t1 = as1; t2 = as2;
+            float ya = df2t_step(xa, t1, t2, ab0, ab1, ab2, aa1, aa2);
+            const bool upd_a = act_a && en_a;
+            as1 = upd_a ? t1 : as1; as2 = upd_a ? t2 : as2;
+            ya_prev = upd_a ? ya : xa;
+            xs[(u + 3) & 3] = __shfl_sync(0xffffffffu, yb, src_lane);
+            if (act_b && last) dst0[nbi] = yb;
+            yl[u] = yb;
+        }
+    };
+    auto ld4 = [&](const float* row, int i) { return *reinterpret_cast<const float4*>(row + (i < B ? i : B - 4)); };
+    // steady-state iterations covering local steps [i0, i1); the group stored by iteration i is dst_at_i0[i - i0 ..]
     auto fast_run = [&](const float* row, int i0, int i1, float* dst_at_i0) {
-        float4 cur = ld4(row, i0);
+        float4 a = ld4(row, i0), b;
+        int i = i0;
 #pragma unroll 1
-        for (int i = i0; i < i1; i += 4) {
-            const int inext = (i + 4 < B) ? i + 4 : i;
-            const float4 nxt = ld4(row, inext);
-            fast4(cur, dst_at_i0 + (i - i0));
-            cur = nxt;
+        for (; i + 8 <= i1; i += 8) {
+            b = ld4(row, i + 4);
+            fast4(a, dst_at_i0 + (i - i0));
+            a = ld4(row, i + 8);
+            fast4(b, dst_at_i0 + (i - i0) + 4);
         }
+        if (i < i1) fast4(a, dst_at_i0 + (i - i0));
     };
 
-    // every valid lane filters and the launch is whole blocks: the chain runs continuously across the launch's blocks,
-    // filling once at the start and draining once at the end
-    const bool all_fast = __all_sync(0xffffffffu, en || !lane_valid);
+    // Every valid band filters and the launch is whole blocks: the chain runs continuously across the launch's blocks,
+    // filling once at the start and draining once at the end.
+    const bool lane_fast = !lane_valid || !do_eq || (en_a && en_b && has_a && has_b);
+    const bool all_fast = __all_sync(0xffffffffu, lane_fast);
     const bool continuous = do_eq && p.tail_frames == B && (SM::kEqWarps > 1 ? __syncthreads_and_eq<SM::kEqThreads>(all_fast) : all_fast);
     float* ring_c = ring_f + (size_t)g * SM::kRingStride + ch * B;  // this chain's channel row of slot 0 (slots are 2*B apart)
     issue_stage(0);
@@ -398,25 +424,26 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
         for (int t = 0; t < p.n_blocks; ++t) {
             wait_stage(t);
             const float* row = stage + ((size_t)(t & 1) * G + g) * SM::kStageStride + ch * B;
-            // part A: the first band starts block t while the last band finishes block t-1
+            // part A (local steps 0..19): the first band starts block t while the last band finishes block t-1
             if (t == 0) {
 #pragma unroll 1
-                for (int i = 0; i < kLag; i += 4) checked4(ld4(row, i), i - D * j, B, ring_c);  // (the last band stores nothing yet)
+                for (int i = 0; i < kLag; i += 4) checked4(ld4(row, i), i - 4 * l, B, ring_c);  // samples 0..2 of block 0 land in slot 0
             } else {
-                float* dprev = ring_c + ((t - 1) % 3) * 2 * B + (B - kLag);
-                fast_run(row, 0, kLag, dprev);
+                fast_run(row, 0, kLag, ring_c + ((t - 1) % 3) * 2 * B + (B - kLag));
                 __threadfence_block();
                 bar_arrive(kBarFull0 + ((t - 1) & 1), kCount);
             }
             if (t >= 2) bar_sync(kBarEmpty0 + (t & 1), kCount);  // ring slot t%3 was last read as history of block t-2
-            // part B: the last band writes the head of block t
+            // part B (local steps 20..B-1): the last band writes samples 0..B-21 of block t
             fast_run(row, kLag, B, ring_c + (t % 3) * 2 * B);
         }
         {
-            // drain: the first band has no more input; band j still owes its last D*j samples
+            // drain: the first band has no more input; flush the three outputs the last fast iteration left pending,
+            // then run the remaining 20 steps checked (sample by sample stores)
             float* dl = ring_c + ((p.n_blocks - 1) % 3) * 2 * B;
+            if (last) { dl[B - 20] = yl[1]; dl[B - 19] = yl[2]; dl[B - 18] = yl[3]; }
 #pragma unroll 1
-            for (int i = 0; i < kLag; i += 4) checked4(make_float4(0.f, 0.f, 0.f, 0.f), B + i - D * j, B, dl);
+            for (int i = 0; i < kLag; i += 4) checked4(make_float4(0.f, 0.f, 0.f, 0.f), B + i - 4 * l, B, dl);
             __threadfence_block();
             bar_arrive(kBarFull0 + ((p.n_blocks - 1) & 1), kCount);
         }
@@ -428,7 +455,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
             const float* st_base = stage + (size_t)(t & 1) * G * SM::kStageStride;
             if (!do_eq) {
-                // EQ off (src/lib.rs:1179): the EQ warps only interleave left/right into the ring
+                // EQ off (src/lib.rs:1179): the EQ warps only move the rows into the ring
                 for (int q = threadIdx.x; q < G * 2 * B; q += SM::kEqThreads) {
                     const int gg = q / (2 * B), n = q - gg * 2 * B;  // n runs over [left row | right row]
                     ring_f[gg * SM::kRingStride + slot * 2 * B + n] = st_base[gg * SM::kStageStride + n];
@@ -438,20 +465,19 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
                 const float* row = st_base + g * SM::kStageStride + ch * B;
                 float* dst = ring_c + slot * 2 * B;
                 xs[0] = xs[1] = xs[2] = xs[3] = 0.f;
+                ya_prev = 0.f;
 #pragma unroll 1
-                for (int i = 0; i < nb + kLag; i += 4) {
+                for (int i = 0; i < nb + kOutLag; i += 4) {
                     const float4 in = (i < B) ? ld4(row, i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    checked4(in, i - D * j, nb, dst);
+                    checked4(in, i - 4 * l, nb, dst);
                 }
             }
             __threadfence_block();
             bar_arrive(kBarFull0 + (t & 1), kCount);
         }
     }
-    if (lane_valid && do_eq && j < p.n_bands) {
-        float* st = reinterpret_cast<float*>(p.eqs + (size_t)s * kMaxBands + j);
-        st[ch] = s1; st[2 + ch] = s2;
-    }
+    if (has_a) { float* st = reinterpret_cast<float*>(p.eqs + (size_t)s * kMaxBands + 2 * l); st[ch] = as1; st[2 + ch] = as2; }
+    if (has_b) { float* st = reinterpret_cast<float*>(p.eqs + (size_t)s * kMaxBands + 2 * l + 1); st[ch] = bs1; st[2 + ch] = bs2; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
