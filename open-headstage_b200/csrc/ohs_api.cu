@@ -646,6 +646,7 @@ int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_
     p.pmax = h->pmax; p.head = h->head; p.n_bands = h->cfg.n_bands;
     p.eq_enable = h->eq_enable && h->cfg.n_bands > 0; p.conv_enable = h->conv_enable;
     p.one = 1.0f;
+    p.zero_mask = 0u;
     OHS_CUDA(cudaEventRecord(h->ev_k0, h->stream));
     rc = launch_render(h, p);
     if (rc) return rc;

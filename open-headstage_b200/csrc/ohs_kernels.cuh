@@ -59,7 +59,8 @@ struct RenderParams {
     int n_bands;
     int eq_enable;
     int conv_enable;
-    float one;                  // 1.0f, deliberately opaque to the compiler (see header comment)
+    float one;                  // 1.0f (kept for ABI stability of the parameter block)
+    unsigned zero_mask;         // 0, deliberately opaque to the compiler: pins instruction order in the EQ loop
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -353,6 +354,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
 
     const int src_lane = (l == 0) ? lane : lane - 1;
     const bool first = (l == 0), last = (l == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
+    const unsigned zmask = p.zero_mask;
     float xs[4] = {0.f, 0.f, 0.f, 0.f};   // band-A inputs of the next steps, shuffled over from lane l-1
     float ya_prev = 0.f;                   // this lane's band-A output of the previous step
     float yl[4] = {0.f, 0.f, 0.f, 0.f};   // band-B outputs of the last four steps (the last lane stores them in groups)
@@ -364,7 +366,11 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
         const float iv[4] = {in.x, in.y, in.z, in.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const float xa = first ? iv[u] : xs[u];
+            // xs[u] was shuffled over three steps ago.  Left alone, ptxas hoists this select to ~23 instructions after
+            // the SHFL and the warp then stalls on the shuffle's real (contended) latency; OR-ing in (previous output &
+            // run-time 0) keeps the value bit-identical but pins its first use to this step.
+            const float xr = __uint_as_float(__float_as_uint(xs[u]) | (__float_as_uint(ya_prev) & zmask));
+            const float xa = first ? iv[u] : xr;
             const float yb = df2t_step(ya_prev, bs1, bs2, bb0, bb1, bb2, ba1, ba2);
             ya_prev = df2t_step(xa, as1, as2, ab0, ab1, ab2, aa1, aa2);
             xs[(u + 3) & 3] = __shfl_sync(0xffffffffu, yb, src_lane);
