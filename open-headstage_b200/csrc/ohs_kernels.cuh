@@ -59,6 +59,7 @@ struct RenderParams {
     int n_bands;
     int eq_enable;
     int conv_enable;
+    int filt_in_smem;           // 0, or the partition count of the single shared HRIR set staged in shared memory
     float one;                  // 1.0f (kept for ABI stability of the parameter block)
     unsigned zero_mask;         // 0, deliberately opaque to the compiler: pins instruction order in the EQ loop
 };
@@ -71,10 +72,11 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 
-// shared-memory index padding: one extra float2 every 8 keeps the stride-8/-64 accesses of the radix passes off the
-// same 64-bit bank
-__host__ __device__ constexpr int padi(int j) { return j + (j >> 3); }
-__host__ __device__ constexpr int padded_len(int n) { return n + (n >> 3); }
+// shared-memory index padding of the complex ping-pong buffers: 16 bytes after every 16 float2.  Adjacent pairs stay
+// contiguous and 16-byte aligned (128-bit accesses), and the strided stores of the radix passes (lane stride 16 float2
+// in the first pass, 64-float2 runs in the second) land on distinct banks.
+__host__ __device__ constexpr int padi(int j) { return j + 2 * (j >> 4); }
+__host__ __device__ constexpr int padded_len(int n) { return n + 2 * (n >> 4); }
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -133,15 +135,21 @@ template <> struct Dft<8> {
 // ---------------------------------------------------------------------------------------------------------------
 // Stockham auto-sort FFT of N complex points by T threads (each thread owns E = N/T points per pass).
 // Pass with radix R after radices of product P:  butterfly i -> k = i mod P, j = (i-k)*R + k,
-//   u[r] = x[i + r*N/R] * w_N^{k r N/(P R)},  y[j + q*P] = DFT_R(u)[q].   Output in natural order.
+//   u[r] = x[i + r*N/R] * w^{k r / (P R)},  y[j + q*P] = DFT_R(u)[q].   Output in natural order.
+// A thread owns ADJACENT butterflies i = tid*PER + b; with an even PER it works on pairs (i, i+1), so every shared
+// memory access moves two float2 in one 128-bit instruction (half the LSU instructions of the 64-bit form) and the
+// two butterflies give the in-order warp two independent dependency chains.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int fft_threads(int n) { return (n / 16 >= 32) ? n / 16 : 32; }
+
 template <int N, int T> struct FftPlan {
-    static constexpr int E = N / T;
-    static_assert(E == 8 || E == 4, "points per thread");
-    static constexpr int R1 = E, P1 = 1;
-    static constexpr int P2 = R1, R2 = (N / P2 >= E) ? E : N / P2;
-    static constexpr int P3 = P2 * R2, R3 = (P3 < N) ? ((N / P3 >= E) ? E : N / P3) : 1;
-    static constexpr int P4 = P3 * R3, R4 = (P4 < N) ? ((N / P4 >= E) ? E : N / P4) : 1;
+    static constexpr int E = N / T;                 // points per thread: 16 (N >= 512), 8 (N = 256), 4 (N = 128)
+    static_assert(E == 16 || E == 8 || E == 4, "points per thread");
+    static constexpr int RM = E < 8 ? E : 8;       // largest radix
+    static constexpr int R1 = RM, P1 = 1;
+    static constexpr int P2 = R1, R2 = (N / P2 >= RM) ? RM : N / P2;
+    static constexpr int P3 = P2 * R2, R3 = (P3 < N) ? ((N / P3 >= RM) ? RM : N / P3) : 1;
+    static constexpr int P4 = P3 * R3, R4 = (P4 < N) ? ((N / P4 >= RM) ? RM : N / P4) : 1;
     static_assert(P4 * R4 == N, "at most four passes");
     static constexpr int kPasses = 2 + (R3 > 1) + (R4 > 1);
     // per-pass twiddle tables, laid out [r-1][k] so that lanes with consecutive k read consecutive float2 (no bank
@@ -155,60 +163,104 @@ template <int N, int T> struct FftPlan {
     static constexpr bool kOutInB0 = (kPasses % 2) == 1;  // which ping-pong buffer a full transform ends in
 };
 
+// padded complex buffer in shared memory; the *2 forms move the adjacent pair (i, i+1), i even, as one float4
+struct SmemCx {
+    float2* p;
+    __device__ __forceinline__ float2 ld(int i) const { return p[padi(i)]; }
+    __device__ __forceinline__ void ld2(int i, float2& a, float2& b) const {
+        const float4 v = *reinterpret_cast<const float4*>(p + padi(i));
+        a = make_float2(v.x, v.y); b = make_float2(v.z, v.w);
+    }
+    __device__ __forceinline__ void st(int i, float2 v) const { p[padi(i)] = v; }
+    __device__ __forceinline__ void st2(int i, float2 a, float2 b) const {
+        *reinterpret_cast<float4*>(p + padi(i)) = make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+
 template <int N, int T, int R, int P, class Load, class Store>
-__device__ __forceinline__ void fft_pass(int tid, const float2* __restrict__ tw, Load load, Store store) {
+__device__ __forceinline__ void fft_pass(int tid, const float2* __restrict__ tw, const Load& load, const Store& store) {
     constexpr int NB = N / R;   // butterflies in this pass
     constexpr int PER = NB / T; // per thread
     static_assert(PER >= 1, "radix larger than points per thread");
+    if constexpr (PER % 2 == 0) {
 #pragma unroll
-    for (int b = 0; b < PER; ++b) {
-        const int i = tid + b * T;
-        const int k = i & (P - 1);
-        const int j = (i - k) * R + k;
-        float2 u[R];
+        for (int b = 0; b < PER; b += 2) {
+            const int i = tid * PER + b;  // even: butterflies i and i+1
+            float2 u[R], v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) u[r] = load(i + r * NB);
-        if (P > 1) {
+            for (int r = 0; r < R; ++r) load.ld2(i + r * NB, u[r], v[r]);
+            if constexpr (P > 1) {
+                const int k = i & (P - 1);  // even, and k+1 < P
 #pragma unroll
-            for (int r = 1; r < R; ++r) u[r] = cmul(u[r], tw[(r - 1) * P + k]);
+                for (int r = 1; r < R; ++r) {
+                    const float4 w = *reinterpret_cast<const float4*>(tw + (r - 1) * P + k);
+                    u[r] = cmul(u[r], make_float2(w.x, w.y));
+                    v[r] = cmul(v[r], make_float2(w.z, w.w));
+                }
+                Dft<R>::run(u);
+                Dft<R>::run(v);
+                const int j = (i - k) * R + k;
+#pragma unroll
+                for (int q = 0; q < R; ++q) store.st2(j + q * P, u[q], v[q]);
+            } else {
+                Dft<R>::run(u);
+                Dft<R>::run(v);
+                // first pass: each butterfly writes R consecutive outputs
+#pragma unroll
+                for (int q = 0; q < R; q += 2) {
+                    store.st2(i * R + q, u[q], u[q + 1]);
+                    store.st2((i + 1) * R + q, v[q], v[q + 1]);
+                }
+            }
         }
-        Dft<R>::run(u);
+    } else {
 #pragma unroll
-        for (int q = 0; q < R; ++q) store(j + q * P, u[q]);
+        for (int b = 0; b < PER; ++b) {
+            const int i = tid * PER + b;
+            const int k = i & (P - 1);
+            const int j = (i - k) * R + k;
+            float2 u[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) u[r] = load.ld(i + r * NB);
+            if constexpr (P > 1) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) u[r] = cmul(u[r], tw[(r - 1) * P + k]);
+            }
+            Dft<R>::run(u);
+#pragma unroll
+            for (int q = 0; q < R; ++q) store.st(j + q * P, u[q]);
+        }
     }
 }
 
 // Full transform.  load0 feeds the first pass, store_last receives the natural-order result, b0/b1 are the ping-pong
 // buffers (padded), `sync` separates passes, `after_first` runs once the first pass has consumed its input.
 template <int N, int T, class Load0, class StoreLast, class Sync, class AfterFirst>
-__device__ __forceinline__ void fft_run(int tid, const float2* __restrict__ tw, float2* b0, float2* b1, Load0 load0,
-                                        StoreLast store_last, Sync sync, AfterFirst after_first) {
+__device__ __forceinline__ void fft_run(int tid, const float2* __restrict__ tw, float2* b0p, float2* b1p, const Load0& load0,
+                                        const StoreLast& store_last, Sync sync, AfterFirst after_first) {
     using Pl = FftPlan<N, T>;
-    auto ld0 = [&](int i) { return b0[padi(i)]; };
-    auto ld1 = [&](int i) { return b1[padi(i)]; };
-    auto st0 = [&](int i, float2 v) { b0[padi(i)] = v; };
-    auto st1 = [&](int i, float2 v) { b1[padi(i)] = v; };
-    fft_pass<N, T, Pl::R1, Pl::P1>(tid, tw, load0, st0);
+    const SmemCx b0{b0p}, b1{b1p};
+    fft_pass<N, T, Pl::R1, Pl::P1>(tid, tw, load0, b0);
     after_first();
     sync();
     if constexpr (Pl::kPasses == 2) {
-        fft_pass<N, T, Pl::R2, Pl::P2>(tid, tw + Pl::kTw2, ld0, store_last);
+        fft_pass<N, T, Pl::R2, Pl::P2>(tid, tw + Pl::kTw2, b0, store_last);
     } else {
-        fft_pass<N, T, Pl::R2, Pl::P2>(tid, tw + Pl::kTw2, ld0, st1);
+        fft_pass<N, T, Pl::R2, Pl::P2>(tid, tw + Pl::kTw2, b0, b1);
         sync();
         if constexpr (Pl::kPasses == 3) {
-            fft_pass<N, T, Pl::R3, Pl::P3>(tid, tw + Pl::kTw3, ld1, store_last);
+            fft_pass<N, T, Pl::R3, Pl::P3>(tid, tw + Pl::kTw3, b1, store_last);
         } else {
-            fft_pass<N, T, Pl::R3, Pl::P3>(tid, tw + Pl::kTw3, ld1, st0);
+            fft_pass<N, T, Pl::R3, Pl::P3>(tid, tw + Pl::kTw3, b1, b0);
             sync();
-            fft_pass<N, T, Pl::R4, Pl::P4>(tid, tw + Pl::kTw4, ld0, store_last);
+            fft_pass<N, T, Pl::R4, Pl::P4>(tid, tw + Pl::kTw4, b0, store_last);
         }
     }
 }
 
 // host side: the per-pass tables for FftPlan<N, T>, f64-computed and rounded once (as rustfft's twiddles are)
 template <int N> inline void fill_twiddles(float2* out) {
-    constexpr int T = (N / 8 >= 32) ? N / 8 : 32;
+    constexpr int T = fft_threads(N);
     using Pl = FftPlan<N, T>;
     const int R[3] = {Pl::R2, Pl::R3, Pl::R4}, P[3] = {Pl::P2, Pl::P3, Pl::P4}, off[3] = {Pl::kTw2, Pl::kTw3, Pl::kTw4};
     for (int i = 0; i < N; ++i) out[i] = make_float2(1.f, 0.f);
@@ -227,7 +279,7 @@ template <int N> inline void fill_twiddles(float2* out) {
 // ---------------------------------------------------------------------------------------------------------------
 template <int N, int G> struct RenderSmem {
     static constexpr int B = N / 2;
-    static constexpr int T = (N / 8 >= 32) ? N / 8 : 32;   // convolution threads per stream
+    static constexpr int T = fft_threads(N);                 // convolution threads per stream (one warp at N <= 512)
     static constexpr int NP = padded_len(N);
     static constexpr int kEqWarps = (G + 2) / 3;             // six (stream, channel) chains of 5 lanes per EQ warp
     static constexpr int kEqThreads = 32 * kEqWarps;
@@ -239,7 +291,10 @@ template <int N, int G> struct RenderSmem {
     static constexpr int kStageStride = 2 * B + 4;   // float per stream and stage buffer: stage[2][G][2][B]
     static constexpr size_t kRingOff = kZOff + sizeof(float2) * G * 2 * NP;
     static constexpr size_t kStageOff = kRingOff + sizeof(float) * G * kRingStride;
-    static constexpr size_t kBytes = kStageOff + sizeof(float) * 2 * G * kStageStride;
+    // filter spectra of a shared single-set, few-partition HRIR (configs 1-3) are staged here once per launch
+    static constexpr size_t kFiltSmemBytes = (N <= 512) ? 16 * 1024 : 0;
+    static constexpr size_t kFiltOff = kStageOff + sizeof(float) * 2 * G * kStageStride;
+    static constexpr size_t kBytes = kFiltOff + kFiltSmemBytes;
     static constexpr bool kFits = kBytes <= 227 * 1024 && kThreads <= 1024;
     // Register budget.  Warps are allocated in groups of four; as many CTAs per SM as shared memory allows (up to
     // four) while every thread keeps at least 80 registers.
@@ -497,6 +552,35 @@ __device__ __forceinline__ void mac_bin(float2& acc, float2 u, float2 pu, float4
     acc.y = fmaf(pu.x, f.w, acc.y); acc.y = fmaf(-pu.y, f.z, acc.y);
 }
 
+// first-pass loader of the forward transform: the overlap-save window [previous block | current block] read from the
+// planar ring, z = left + i*right
+struct RingWindow {
+    const float* xp; const float* xc; int B;
+    __device__ __forceinline__ float2 ld(int i) const {
+        return i < B ? make_float2(xp[i], xp[B + i]) : make_float2(xc[i - B], xc[i]);
+    }
+    __device__ __forceinline__ void ld2(int i, float2& a, float2& b) const {  // i even: samples i and i+1
+        const float* row = i < B ? xp + i : xc + (i - B);
+        const float2 l = *reinterpret_cast<const float2*>(row), r = *reinterpret_cast<const float2*>(row + B);
+        a = make_float2(l.x, r.x); b = make_float2(l.y, r.y);
+    }
+};
+
+// last-pass store of the inverse transform (run as swap o FFT o swap): keep the last B samples, left = Im, right = Re
+// of the swapped result, times the gain; coalesced stores straight to the output rows
+struct OutputStore {
+    float* ol; float* orr; float gain; int B;  // ol/orr already offset by -B
+    __device__ __forceinline__ void st(int i, float2 v) const {
+        if (i >= B) { ol[i] = v.y * gain; orr[i] = v.x * gain; }
+    }
+    __device__ __forceinline__ void st2(int i, float2 a, float2 b) const {  // i even
+        if (i >= B) {
+            *reinterpret_cast<float2*>(ol + i) = make_float2(a.y * gain, b.y * gain);
+            *reinterpret_cast<float2*>(orr + i) = make_float2(a.x * gain, b.x * gain);
+        }
+    }
+};
+
 template <int N, int G>
 __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned char* smem, int stream0) {
     using SM = RenderSmem<N, G>;
@@ -512,8 +596,8 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     const bool valid = s < p.n_streams;
     float2* b0 = reinterpret_cast<float2*>(smem + SM::kZOff) + (size_t)g * 2 * NP;
     float2* b1 = b0 + NP;
-    float2* zbuf = Pl::kOutInB0 ? b0 : b1;   // forward transform lands here
-    float2* wbuf = Pl::kOutInB0 ? b1 : b0;   // frequency-domain product goes here
+    const SmemCx zbuf{Pl::kOutInB0 ? b0 : b1};   // forward transform lands here
+    const SmemCx wbuf{Pl::kOutInB0 ? b1 : b0};   // frequency-domain product goes here
     float* ring_g = ring + (size_t)g * SM::kRingStride;  // planar: slot k = [left row | right row] at k*2*B
 
     int nparts = 1;
@@ -523,7 +607,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     if (valid) {
         const int set = p.stream_hrir[s];
         nparts = p.set_parts[set];
-        filt = p.filt + (size_t)set * p.pmax * N;
+        filt = p.filt_in_smem ? reinterpret_cast<const float4*>(smem + SM::kFiltOff) : p.filt + (size_t)set * p.pmax * N;
         gain = p.stream_gain[s];
         fdl_s = p.fdl + (size_t)s * p.pmax * N;
     }
@@ -552,60 +636,71 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
             continue;
         }
         // ---- forward FFT of the overlap-save window [previous block | current block], z = left + i*right
-        fft_run<N, T>(
-            tid, tw, b0, b1, [&](int i) { return i < B ? make_float2(xp[i], xp[B + i]) : make_float2(xc[i - B], xc[i]); },
-            [&](int i, float2 v) { zbuf[padi(i)] = v; }, stream_sync,
-            [&]() { if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount); });
+        fft_run<N, T>(tid, tw, b0, b1, RingWindow{xp, xc, B}, zbuf, stream_sync,
+                      [&]() { if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount); });
         stream_sync();
-        // ---- frequency-domain delay line + 4-path multiply-accumulate
+        // ---- frequency-domain delay line + 4-path multiply-accumulate.  A thread owns adjacent bins (k, k+1), k even,
+        // k < N/2, and their mirror bins N-k, N-k-1 (bin 0 pairs with itself, and N/2 rides along with it).
         int slot = p.head + t;
         slot -= (slot / p.pmax) * p.pmax;
         if (nparts > 1) {
-            float2* dstz = fdl_s + (size_t)slot * N;
+            float4* dstz = reinterpret_cast<float4*>(fdl_s + (size_t)slot * N);
 #pragma unroll
-            for (int e = 0; e < N / T; ++e) { const int i = tid + e * T; dstz[i] = zbuf[padi(i)]; }
+            for (int e = 0; e < N / 2 / T; ++e) {
+                const int i = 2 * (tid + e * T);
+                float2 z0, z1;
+                zbuf.ld2(i, z0, z1);
+                dstz[i >> 1] = make_float4(z0.x, z0.y, z1.x, z1.y);
+            }
         }
-        constexpr int kItems = N / 2 / T;
-        float2 acc_a[kItems], acc_b[kItems];
+        constexpr int kPairs = N / 4 / T;
+        float2 acc[kPairs][4];  // W[k], W[k+1], W[mirror(k)], W[mirror(k+1)]
 #pragma unroll
-        for (int m = 0; m < kItems; ++m) {
-            const int k = tid + m * T;
-            const int ka = k, kb = k ? N - k : N / 2;
-            const float2 u = zbuf[padi(ka)], v = zbuf[padi(kb)];
-            const float4 fa = __ldg(filt + ka), fb = __ldg(filt + kb);
-            acc_a[m] = make_float2(0.f, 0.f); acc_b[m] = make_float2(0.f, 0.f);
-            mac_bin(acc_a[m], u, k ? v : u, fa);
-            mac_bin(acc_b[m], v, k ? u : v, fb);
+        for (int m = 0; m < kPairs; ++m) {
+            const int k = 2 * (tid + m * T);
+            const int m0 = k ? N - k : N / 2, m1 = N - k - 1;
+            float2 u0, u1;
+            zbuf.ld2(k, u0, u1);
+            const float2 v0 = zbuf.ld(m0), v1 = zbuf.ld(m1);
+            const float4 f0 = filt[k], f1 = filt[k + 1], g0 = filt[m0], g1 = filt[m1];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[m][e] = make_float2(0.f, 0.f);
+            mac_bin(acc[m][0], u0, k ? v0 : u0, f0);
+            mac_bin(acc[m][1], u1, v1, f1);
+            mac_bin(acc[m][2], v0, k ? u0 : v0, g0);
+            mac_bin(acc[m][3], v1, u1, g1);
         }
         for (int q = 1; q < nparts; ++q) {
             int sl = slot - q; if (sl < 0) sl += p.pmax;
             const float2* zq = fdl_s + (size_t)sl * N;
             const float4* fq = filt + (size_t)q * N;
 #pragma unroll
-            for (int m = 0; m < kItems; ++m) {
-                const int k = tid + m * T;
-                const int ka = k, kb = k ? N - k : N / 2;
-                const float2 u = zq[ka], v = zq[kb];
-                const float4 fa = __ldg(fq + ka), fb = __ldg(fq + kb);
-                mac_bin(acc_a[m], u, k ? v : u, fa);
-                mac_bin(acc_b[m], v, k ? u : v, fb);
+            for (int m = 0; m < kPairs; ++m) {
+                const int k = 2 * (tid + m * T);
+                const int m0 = k ? N - k : N / 2, m1 = N - k - 1;
+                const float4 uu = *reinterpret_cast<const float4*>(zq + k);
+                const float2 u0 = make_float2(uu.x, uu.y), u1 = make_float2(uu.z, uu.w);
+                const float2 v0 = zq[m0], v1 = zq[m1];
+                const float4 f0 = fq[k], f1 = fq[k + 1], g0 = fq[m0], g1 = fq[m1];
+                mac_bin(acc[m][0], u0, k ? v0 : u0, f0);
+                mac_bin(acc[m][1], u1, v1, f1);
+                mac_bin(acc[m][2], v0, k ? u0 : v0, g0);
+                mac_bin(acc[m][3], v1, u1, g1);
             }
         }
 #pragma unroll
-        for (int m = 0; m < kItems; ++m) {
-            const int k = tid + m * T;
-            const int ka = k, kb = k ? N - k : N / 2;
+        for (int m = 0; m < kPairs; ++m) {
+            const int k = 2 * (tid + m * T);
+            const int m0 = k ? N - k : N / 2, m1 = N - k - 1;
             // swap(re, im): the inverse transform is run as swap(FFT(swap(W)))
-            wbuf[padi(ka)] = make_float2(acc_a[m].y, acc_a[m].x);
-            wbuf[padi(kb)] = make_float2(acc_b[m].y, acc_b[m].x);
+            wbuf.st2(k, make_float2(acc[m][0].y, acc[m][0].x), make_float2(acc[m][1].y, acc[m][1].x));
+            wbuf.st(m0, make_float2(acc[m][2].y, acc[m][2].x));
+            wbuf.st(m1, make_float2(acc[m][3].y, acc[m][3].x));
         }
         stream_sync();
         // ---- inverse FFT; keep the last B samples (overlap-save), ear sums are already inside W, apply gain
-        float* ol = out_l + (size_t)t * B - B;
-        float* orr = out_r + (size_t)t * B - B;
-        fft_run<N, T>(
-            tid, tw, zbuf, wbuf, [&](int i) { return wbuf[padi(i)]; },
-            [&](int i, float2 v) { if (i >= B) { ol[i] = v.y * gain; orr[i] = v.x * gain; } }, stream_sync, [&]() {});
+        fft_run<N, T>(tid, tw, zbuf.p, wbuf.p, wbuf, OutputStore{out_l + (size_t)t * B - B, out_r + (size_t)t * B - B, gain, B},
+                      stream_sync, [&]() {});
     }
     // overlap-save history for the next launch: the last filtered block
     if (valid && p.conv_enable && p.n_blocks > 0) {
@@ -631,6 +726,12 @@ __global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const Re
             ring[g * SM::kRingStride + 2 * 2 * SM::B + n] = v.x;
             ring[g * SM::kRingStride + 2 * 2 * SM::B + SM::B + n] = v.y;
         }
+        if (p.filt_in_smem) {
+            // one shared HRIR set with few partitions: its spectra stay in shared memory for the whole launch
+            float4* fs = reinterpret_cast<float4*>(smem + SM::kFiltOff);
+            const int n4 = p.filt_in_smem * N;  // partitions * N
+            for (int i = threadIdx.x; i < n4; i += SM::kThreads) fs[i] = p.filt[i];
+        }
     }
     __syncthreads();
     if (threadIdx.x < SM::kEqThreads) eq_warp_main<N, G>(p, smem, stream0, threadIdx.x >> 5);
@@ -642,9 +743,16 @@ __global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const Re
 // ir: [set][4][pmax*B] zero-padded time-domain taps; filt: [set][pmax][N]
 // ---------------------------------------------------------------------------------------------------------------
 template <int N> struct SetupSmem {
-    static constexpr int T = (N / 8 >= 32) ? N / 8 : 32;
+    static constexpr int T = fft_threads(N);
     static constexpr int NP = padded_len(N);
     static constexpr size_t kBytes = sizeof(float2) * (N + 4 * NP);
+};
+
+// first-pass loader: an impulse-response chunk of two paths as (re, im), zero-padded from B to N (:123-129)
+struct IrChunk {
+    const float* ha; const float* hb; int B;
+    __device__ __forceinline__ float2 ld(int i) const { return i < B ? make_float2(ha[i], hb[i]) : make_float2(0.f, 0.f); }
+    __device__ __forceinline__ void ld2(int i, float2& a, float2& b) const { a = ld(i); b = ld(i + 1); }
 };
 
 template <int N>
@@ -670,20 +778,15 @@ __global__ void __launch_bounds__(SetupSmem<N>::T) setup_filters_kernel(const fl
     const float* h = ir + (size_t)set * 4 * pmax * B + (size_t)part * B;
     const size_t ps = (size_t)pmax * B;  // path stride
     auto sync = [&]() { __syncthreads(); };
-    float2* gl = Pl::kOutInB0 ? a0 : a1;
-    float2* gr = Pl::kOutInB0 ? c0 : c1;
-    // G_L = FFT(h_LSL + i h_LSR), G_R = FFT(h_RSL + i h_RSR), each chunk zero-padded to N (:123-129)
-    fft_run<N, T>(
-        tid, tw, a0, a1, [&](int i) { return i < B ? make_float2(h[i], h[ps + i]) : make_float2(0.f, 0.f); },
-        [&](int i, float2 v) { gl[padi(i)] = v; }, sync, [&]() {});
-    fft_run<N, T>(
-        tid, tw, c0, c1, [&](int i) { return i < B ? make_float2(h[2 * ps + i], h[3 * ps + i]) : make_float2(0.f, 0.f); },
-        [&](int i, float2 v) { gr[padi(i)] = v; }, sync, [&]() {});
+    const SmemCx gl{Pl::kOutInB0 ? a0 : a1}, gr{Pl::kOutInB0 ? c0 : c1};
+    // G_L = FFT(h_LSL + i h_LSR), G_R = FFT(h_RSL + i h_RSR)
+    fft_run<N, T>(tid, tw, a0, a1, IrChunk{h, h + ps, B}, gl, sync, [&]() {});
+    fft_run<N, T>(tid, tw, c0, c1, IrChunk{h + 2 * ps, h + 3 * ps, B}, gr, sync, [&]() {});
     __syncthreads();
     const float sc = 1.0f / (2.0f * (float)N);  // 1/2 of the real/imag split and the 1/FFT_SIZE of :280, exact power of two
     float4* dst = filt + ((size_t)set * pmax + part) * N;
     for (int k = tid; k < N; k += T) {
-        const float2 l = gl[padi(k)], r = gr[padi(k)];
+        const float2 l = gl.ld(k), r = gr.ld(k);
         dst[k] = make_float4((l.x + r.y) * sc, (l.y - r.x) * sc, (l.x - r.y) * sc, (l.y + r.x) * sc);
     }
 }
