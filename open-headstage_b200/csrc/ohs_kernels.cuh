@@ -27,6 +27,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 namespace ohs {
 
 constexpr int kMaxBands = 10;
@@ -283,7 +285,33 @@ template <int N, int G> struct RenderSmem {
     static constexpr int NP = padded_len(N);
     static constexpr int kEqWarps = (G + 2) / 3;             // six (stream, channel) chains of 5 lanes per EQ warp
     static constexpr int kEqThreads = 32 * kEqWarps;
-    static constexpr int kThreads = kEqThreads + G * T;
+    static constexpr int kConvWarps = G * T / 32;
+    static constexpr int kWorkers = kEqThreads + G * T;       // threads that take part in the named barriers
+    // Warp placement.  A warp's scheduler partition is (warp id mod 4) and an EQ warp carries about four times the
+    // instructions of a convolution warp, so the roles are spread to equalise the partitions' load: EQ warp w sits on
+    // partition w (warp id w); each convolution warp goes to the least-loaded partition; unused warp slots exit at
+    // once.  (Config 2, G = 7: partitions 0-2 hold one EQ + one convolution warp, partition 3 four convolution warps.)
+    struct Placement {
+        int conv_warp_id[kConvWarps > 0 ? kConvWarps : 1];
+        int total_warps;
+    };
+    static constexpr Placement place() {
+        Placement pl{};
+        int load[4] = {0, 0, 0, 0}, count[4] = {0, 0, 0, 0};
+        for (int w = 0; w < kEqWarps; ++w) { load[w & 3] += 4; count[w & 3] += 1; }
+        for (int f = 0; f < kConvWarps; ++f) {
+            int best = 3;
+            for (int q = 3; q >= 0; --q) if (load[q] < load[best]) best = q;
+            pl.conv_warp_id[f] = 4 * count[best] + best;
+            load[best] += 1; count[best] += 1;
+        }
+        int mx = 0;
+        for (int q = 0; q < 4; ++q) if (count[q] > mx) mx = count[q];
+        pl.total_warps = 4 * mx;
+        return pl;
+    }
+    static constexpr int kThreads = 32 * place().total_warps;
+    template <int F> static constexpr int kConvWarpId = place().conv_warp_id[F];
     static constexpr size_t kTwOff = 0;                                      // float2 tw[N]
     static constexpr size_t kZOff = kTwOff + sizeof(float2) * N;             // float2 z[G][2][NP]
     // per-stream strides carry a 16-byte pad so that neighbouring streams sit on different banks
@@ -298,7 +326,7 @@ template <int N, int G> struct RenderSmem {
     static constexpr bool kFits = kBytes <= 227 * 1024 && kThreads <= 1024;
     // Register budget.  Warps are allocated in groups of four; as many CTAs per SM as shared memory allows (up to
     // four) while every thread keeps at least 80 registers.
-    static constexpr int kWarpsAlloc = (kThreads / 32 + 3) / 4 * 4;
+    static constexpr int kWarpsAlloc = kThreads / 32;  // already a multiple of four
     static constexpr int kBySmem = (int)((227 * 1024) / (kBytes + 1024));
     static constexpr int kByRegs = 65536 / (80 * 32 * kWarpsAlloc);
     static constexpr int kMinBlocks0 = kBySmem < kByRegs ? kBySmem : kByRegs;
@@ -339,7 +367,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     constexpr int kOutLag = 4 * (kEqGroup - 1) + 1;  // 17: steps the last band runs behind the first
     constexpr int kLag = 20;                          // kOutLag rounded to whole 4-step iterations (16-byte stores)
     static_assert(kEqSkew == 4 && kEqGroup == 5 && kOutLag == 17 && (B - kLag) % 4 == 0 && B >= 2 * kLag, "systolic loop layout");
-    constexpr int kCount = SM::kThreads;
+    constexpr int kCount = SM::kWorkers;
     float* ring_f = reinterpret_cast<float*>(smem + SM::kRingOff);
     float* stage = reinterpret_cast<float*>(smem + SM::kStageOff);
 
@@ -582,15 +610,15 @@ struct OutputStore {
 };
 
 template <int N, int G>
-__device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned char* smem, int stream0) {
+__device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned char* smem, int stream0, int conv_index) {
     using SM = RenderSmem<N, G>;
     constexpr int B = SM::B, T = SM::T, NP = SM::NP;
-    constexpr int kCount = SM::kThreads;
+    constexpr int kCount = SM::kWorkers;
     using Pl = FftPlan<N, T>;
     const float2* tw = reinterpret_cast<const float2*>(smem + SM::kTwOff);
     float* ring = reinterpret_cast<float*>(smem + SM::kRingOff);
 
-    const int ft = threadIdx.x - SM::kEqThreads;
+    const int ft = conv_index * 32 + (threadIdx.x & 31);
     const int g = ft / T, tid = ft - g * T;
     const int s = stream0 + g;
     const bool valid = s < p.n_streams;
@@ -709,6 +737,14 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     }
 }
 
+// which convolution warp (if any) the placement puts on hardware warp slot `warp`
+template <int N, int G, int... F>
+__device__ __forceinline__ int find_conv_index(int warp, std::integer_sequence<int, F...>) {
+    int r = -1;
+    ((RenderSmem<N, G>::template kConvWarpId<F> == warp ? (void)(r = F) : (void)0), ...);
+    return r;
+}
+
 template <int N, int G>
 __global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const RenderParams p) {
     using SM = RenderSmem<N, G>;
@@ -734,8 +770,10 @@ __global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const Re
         }
     }
     __syncthreads();
-    if (threadIdx.x < SM::kEqThreads) eq_warp_main<N, G>(p, smem, stream0, threadIdx.x >> 5);
-    else conv_warps_main<N, G>(p, smem, stream0);
+    const int warp = threadIdx.x >> 5;
+    if (warp < SM::kEqWarps) { eq_warp_main<N, G>(p, smem, stream0, warp); return; }
+    const int conv_index = find_conv_index<N, G>(warp, std::make_integer_sequence<int, SM::kConvWarps>{});
+    if (conv_index >= 0) conv_warps_main<N, G>(p, smem, stream0, conv_index);  // other warp slots are placement padding
 }
 
 // ---------------------------------------------------------------------------------------------------------------
