@@ -34,7 +34,8 @@ namespace ohs {
 constexpr int kMaxBands = 10;
 constexpr int kEqGroup = 5;    // lanes per (stream, channel) chain in an EQ warp: two bands per lane
 constexpr int kMaxG = 7;       // streams per CTA; their 2G chains of 5 lanes are spread over ceil(G/3) EQ warps
-constexpr int kEqSkew = 4;     // samples between neighbouring lanes of the systolic chain (hides the 26-cycle SHFL)
+constexpr int kEqSkew = 8;     // steps between neighbouring lanes of the systolic chain: a shuffled value is consumed 7 steps
+                               // (~200 cycles) after it was sent, which rides out shared-memory-pipe contention from the FFT warps
 constexpr int kEqCoefStride = 8;  // floats per (eq_set, band): b0 b1 b2 a1 a2 enabled pad pad
 
 enum NamedBarrier { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarEq = 5, kBarStream0 = 6 };
@@ -364,9 +365,12 @@ template <int N, int G>
 __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned char* smem, int stream0, int w) {
     using SM = RenderSmem<N, G>;
     constexpr int B = SM::B;
-    constexpr int kOutLag = 4 * (kEqGroup - 1) + 1;  // 17: steps the last band runs behind the first
-    constexpr int kLag = 20;                          // kOutLag rounded to whole 4-step iterations (16-byte stores)
-    static_assert(kEqSkew == 4 && kEqGroup == 5 && kOutLag == 17 && (B - kLag) % 4 == 0 && B >= 2 * kLag, "systolic loop layout");
+    constexpr int DL = kEqSkew;                        // lane skew in steps = steps per unrolled iteration
+    constexpr int NQ = DL / 4;                         // float4 input loads per iteration
+    constexpr int kOutLag = DL * (kEqGroup - 1) + 1;   // steps the last band runs behind the first (33)
+    constexpr int kGrp = kOutLag + 3;                  // the group stored at local step i is samples [i-kGrp, i-kGrp+3]
+    constexpr int kLagA = (kGrp + DL - 1) / DL * DL;   // steps of a block during which the previous block is still being finished
+    static_assert((DL == 4 || DL == 8) && kEqGroup == 5 && kGrp % 4 == 0 && B % DL == 0 && B >= kLagA, "systolic loop layout");
     constexpr int kCount = SM::kWorkers;
     float* ring_f = reinterpret_cast<float*>(smem + SM::kRingOff);
     float* stage = reinterpret_cast<float*>(smem + SM::kStageOff);
@@ -438,40 +442,46 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     const int src_lane = (l == 0) ? lane : lane - 1;
     const bool first = (l == 0), last = (l == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
     const unsigned zmask = p.zero_mask;
-    float xs[4] = {0.f, 0.f, 0.f, 0.f};   // band-A inputs of the next steps, shuffled over from lane l-1
-    float ya_prev = 0.f;                   // this lane's band-A output of the previous step
-    float yl[4] = {0.f, 0.f, 0.f, 0.f};   // band-B outputs of the last four steps (the last lane stores them in groups)
-
-    // Four steady-state steps (local steps i0 .. i0+3): every lane holds live samples (lanes of absent streams run on
-    // garbage that is never stored).  At the first of the four steps the last lane completes an aligned group of four
-    // output samples, [i0-20, i0-17] of the block being written, and stores it with one 16-byte store.
-    auto fast4 = [&](float4 in, float* dst_group) {
-        const float iv[4] = {in.x, in.y, in.z, in.w};
+    float xs[DL], yl[DL];  // xs: band-A inputs of the next DL steps, shuffled over from lane l-1;  yl: last DL band-B outputs
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            // xs[u] was shuffled over three steps ago.  Left alone, ptxas hoists this select to ~23 instructions after
+    for (int u = 0; u < DL; ++u) { xs[u] = 0.f; yl[u] = 0.f; }
+    float ya_prev = 0.f;   // this lane's band-A output of the previous step
+    struct In { float4 q[NQ]; };
+    auto in_at = [&](const In& in, int u) { const float4 v = in.q[u >> 2]; return (u & 3) == 0 ? v.x : (u & 3) == 1 ? v.y : (u & 3) == 2 ? v.z : v.w; };
+
+    // DL steady-state steps (local steps i0 .. i0+DL-1): every lane holds live samples (lanes of absent streams run on
+    // garbage that is never stored).  Whenever the last lane has completed an aligned group of four output samples
+    // ([i-kGrp, i-kGrp+3] at local step i, i % 4 == 0) it stores the group with one 16-byte store — into the previous
+    // block's ring slot while the group index is negative, into the current block's afterwards.
+    auto fast_iter = [&](const In& in, int i0, float* dprev_end, float* dcur) {
+#pragma unroll
+        for (int u = 0; u < DL; ++u) {
+            // xs[u] was shuffled over DL-1 steps ago.  Left alone, ptxas hoists this select to ~23 instructions after
             // the SHFL and the warp then stalls on the shuffle's real (contended) latency; OR-ing in (previous output &
             // run-time 0) keeps the value bit-identical but pins its first use to this step.
             const float xr = __uint_as_float(__float_as_uint(xs[u]) | (__float_as_uint(ya_prev) & zmask));
-            const float xa = first ? iv[u] : xr;
+            const float xa = first ? in_at(in, u) : xr;
             const float yb = df2t_step(ya_prev, bs1, bs2, bb0, bb1, bb2, ba1, ba2);
             ya_prev = df2t_step(xa, as1, as2, ab0, ab1, ab2, aa1, aa2);
-            xs[(u + 3) & 3] = __shfl_sync(0xffffffffu, yb, src_lane);
-            if (u == 0 && last) *reinterpret_cast<float4*>(dst_group) = make_float4(yl[1], yl[2], yl[3], yb);
+            xs[(u + DL - 1) % DL] = __shfl_sync(0xffffffffu, yb, src_lane);
+            if ((u & 3) == 0 && last) {
+                const int g0 = i0 + u - kGrp;
+                float* dstp = (g0 < 0 ? dprev_end : dcur) + g0;
+                *reinterpret_cast<float4*>(dstp) = make_float4(yl[(u + DL - 3) % DL], yl[(u + DL - 2) % DL], yl[(u + DL - 1) % DL], yb);
+            }
             yl[u] = yb;
         }
     };
-    // Four checked steps (pipeline fill and drain, ragged blocks, disabled bands): state and outputs are committed only
+    // DL checked steps (pipeline fill and drain, ragged blocks, disabled bands): state and outputs are committed only
     // where a band holds a live sample; a disabled band passes its input through and keeps its state
-    // (src/dsp/parametric_eq.rs:118-120).  na0 = band A's sample index at the first of the four steps; live samples
+    // (src/dsp/parametric_eq.rs:118-120).  na0 = band A's sample index at the first of the steps; live samples
     // are [0, nb); the last lane stores sample by sample into dst0[n].
-    auto checked4 = [&](float4 in, int na0, int nb, float* dst0) {
-        const float iv[4] = {in.x, in.y, in.z, in.w};
+    auto checked_iter = [&](const In& in, int na0, int nb, float* dst0) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < DL; ++u) {
             const int na = na0 + u, nbi = na - 1;
             const bool act_a = lane_valid && na >= 0 && na < nb, act_b = lane_valid && nbi >= 0 && nbi < nb;
-            const float xa = first ? iv[u] : xs[u];
+            const float xa = first ? in_at(in, u) : xs[u];
             float t1 = bs1, t2 = bs2;
             float yb = df2t_step(ya_prev, t1, t2, bb0, bb1, bb2, ba1, ba2);
             const bool upd_b = act_b && en_b;
@@ -482,24 +492,31 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             const bool upd_a = act_a && en_a;
             as1 = upd_a ? t1 : as1; as2 = upd_a ? t2 : as2;
             ya_prev = upd_a ? ya : xa;
-            xs[(u + 3) & 3] = __shfl_sync(0xffffffffu, yb, src_lane);
+            xs[(u + DL - 1) % DL] = __shfl_sync(0xffffffffu, yb, src_lane);
             if (act_b && last) dst0[nbi] = yb;
             yl[u] = yb;
         }
     };
-    auto ld4 = [&](const float* row, int i) { return *reinterpret_cast<const float4*>(row + (i < B ? i : B - 4)); };
-    // steady-state iterations covering local steps [i0, i1); the group stored by iteration i is dst_at_i0[i - i0 ..]
-    auto fast_run = [&](const float* row, int i0, int i1, float* dst_at_i0) {
-        float4 a = ld4(row, i0), b;
+    // input samples [i, i+DL) of a staged row (zeros past the end of the block)
+    auto ld_in = [&](const float* row, int i) {
+        In in;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+            in.q[q] = (i + 4 * q < B) ? *reinterpret_cast<const float4*>(row + i + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return in;
+    };
+    // steady-state iterations covering local steps [i0, i1); inputs are loaded one iteration ahead
+    auto fast_run = [&](const float* row, int i0, int i1, float* dprev_end, float* dcur) {
+        In a = ld_in(row, i0), b;
         int i = i0;
 #pragma unroll 1
-        for (; i + 8 <= i1; i += 8) {
-            b = ld4(row, i + 4);
-            fast4(a, dst_at_i0 + (i - i0));
-            a = ld4(row, i + 8);
-            fast4(b, dst_at_i0 + (i - i0) + 4);
+        for (; i + 2 * DL <= i1; i += 2 * DL) {
+            b = ld_in(row, i + DL);
+            fast_iter(a, i, dprev_end, dcur);
+            a = ld_in(row, i + 2 * DL);
+            fast_iter(b, i + DL, dprev_end, dcur);
         }
-        if (i < i1) fast4(a, dst_at_i0 + (i - i0));
+        if (i < i1) fast_iter(a, i, dprev_end, dcur);
     };
 
     // Every valid band filters and the launch is whole blocks: the chain runs continuously across the launch's blocks,
@@ -512,27 +529,34 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     if (continuous) {
         for (int t = 0; t < p.n_blocks; ++t) {
             wait_stage(t);
+            if (t >= 2) bar_sync(kBarEmpty0 + (t & 1), kCount);  // ring slot t%3 was last read as history of block t-2
             const float* row = stage + ((size_t)(t & 1) * G + g) * SM::kStageStride + ch * B;
-            // part A (local steps 0..19): the first band starts block t while the last band finishes block t-1
+            float* dcur = ring_c + (t % 3) * 2 * B;
+            float* dprev_end = ring_c + ((t + 2) % 3) * 2 * B + B;  // one past the previous block's row
+            // first kLagA steps: the first band starts block t while the last band finishes block t-1
             if (t == 0) {
 #pragma unroll 1
-                for (int i = 0; i < kLag; i += 4) checked4(ld4(row, i), i - 4 * l, B, ring_c);  // samples 0..2 of block 0 land in slot 0
+                for (int i = 0; i < kLagA; i += DL) checked_iter(ld_in(row, i), i - DL * l, B, dcur);
             } else {
-                fast_run(row, 0, kLag, ring_c + ((t - 1) % 3) * 2 * B + (B - kLag));
+                fast_run(row, 0, kLagA, dprev_end, dcur);
                 __threadfence_block();
                 bar_arrive(kBarFull0 + ((t - 1) & 1), kCount);
             }
-            if (t >= 2) bar_sync(kBarEmpty0 + (t & 1), kCount);  // ring slot t%3 was last read as history of block t-2
-            // part B (local steps 20..B-1): the last band writes samples 0..B-21 of block t
-            fast_run(row, kLag, B, ring_c + (t % 3) * 2 * B);
+            fast_run(row, kLagA, B, dprev_end, dcur);
         }
         {
             // drain: the first band has no more input; flush the three outputs the last fast iteration left pending,
-            // then run the remaining 20 steps checked (sample by sample stores)
+            // then run the remaining steps checked (sample by sample stores)
             float* dl = ring_c + ((p.n_blocks - 1) % 3) * 2 * B;
-            if (last) { dl[B - 20] = yl[1]; dl[B - 19] = yl[2]; dl[B - 18] = yl[3]; }
+            if (last) {
+#pragma unroll
+                for (int e = 0; e < 3; ++e) dl[B - 1 - kOutLag - 2 + e] = yl[DL - 3 + e];
+            }
+            In zero;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) zero.q[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-            for (int i = 0; i < kLag; i += 4) checked4(make_float4(0.f, 0.f, 0.f, 0.f), B + i - 4 * l, B, dl);
+            for (int i = 0; i < kOutLag; i += DL) checked_iter(zero, B + i - DL * l, B, dl);
             __threadfence_block();
             bar_arrive(kBarFull0 + ((p.n_blocks - 1) & 1), kCount);
         }
@@ -553,13 +577,11 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
                 // per-block chain (ragged last block and/or disabled bands): fill, run and drain inside the block
                 const float* row = st_base + g * SM::kStageStride + ch * B;
                 float* dst = ring_c + slot * 2 * B;
-                xs[0] = xs[1] = xs[2] = xs[3] = 0.f;
+#pragma unroll
+                for (int u = 0; u < DL; ++u) xs[u] = 0.f;
                 ya_prev = 0.f;
 #pragma unroll 1
-                for (int i = 0; i < nb + kOutLag; i += 4) {
-                    const float4 in = (i < B) ? ld4(row, i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    checked4(in, i - 4 * l, nb, dst);
-                }
+                for (int i = 0; i < nb + kOutLag; i += DL) checked_iter(ld_in(row, i), i - DL * l, nb, dst);
             }
             __threadfence_block();
             bar_arrive(kBarFull0 + (t & 1), kCount);
