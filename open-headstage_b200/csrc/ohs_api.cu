@@ -714,8 +714,9 @@ int ohs_process(ohs_engine* h, const float* in, float* out, size_t n_frames, siz
         if (in != out) for (size_t r = 0; r < rows; ++r) memcpy(out + r * row_stride, in + r * row_stride, n_frames * sizeof(float));
         return OHS_OK;
     }
-    // chunk: whole blocks, about 48 MiB per staging buffer, at least one block
-    const size_t target_bytes = (size_t)48 << 20;
+    // chunk: whole blocks, about 24 MiB per staging buffer, at least one block
+    size_t target_bytes = (size_t)24 << 20;  // measured best on PCIe Gen5 x16 with both directions busy (tools/e2e_probe.py)
+    if (const char* e = getenv("OHS_STAGE_MB")) { const long mb = atol(e); if (mb >= 1 && mb <= 4096) target_bytes = (size_t)mb << 20; }
     size_t chunk = target_bytes / (rows * sizeof(float));
     chunk = std::max<size_t>(h->B, (chunk / h->B) * h->B);
     chunk = std::min(chunk, (n_frames + 3) / 4 * 4);

@@ -32,7 +32,12 @@
 namespace ohs {
 
 constexpr int kMaxBands = 10;
-constexpr int kEqGroup = 5;    // lanes per (stream, channel) chain in an EQ warp: two bands per lane
+// Two bands per lane: five lanes per chain, three EQ warps for seven streams (one per scheduler partition).  One band
+// per lane (ten lanes, five EQ warps) was measured too: two EQ warps then share a partition and the block time is the
+// same (844 k vs 852 k stream-s/s), for more issue slots.
+constexpr int kEqBandsPerLane = 2;
+constexpr int kEqGroup = kMaxBands / kEqBandsPerLane;  // lanes per (stream, channel) chain in an EQ warp
+constexpr int kEqChainsPerWarp = 32 / kEqGroup;
 constexpr int kMaxG = 7;       // streams per CTA; their 2G chains of 5 lanes are spread over ceil(G/3) EQ warps
 constexpr int kEqSkew = 8;     // steps between neighbouring lanes of the systolic chain: a shuffled value is consumed 7 steps
                                // (~200 cycles) after it was sent, which rides out shared-memory-pipe contention from the FFT warps
@@ -284,11 +289,11 @@ template <int N, int G> struct RenderSmem {
     static constexpr int B = N / 2;
     static constexpr int T = fft_threads(N);                 // convolution threads per stream (one warp at N <= 512)
     static constexpr int NP = padded_len(N);
-    static constexpr int kEqWarps = (G + 2) / 3;             // six (stream, channel) chains of 5 lanes per EQ warp
+    static constexpr int kEqWarps = (2 * G + kEqChainsPerWarp - 1) / kEqChainsPerWarp;  // 3 (or 6) chains per EQ warp
     static constexpr int kEqThreads = 32 * kEqWarps;
     static constexpr int kConvWarps = G * T / 32;
     static constexpr int kWorkers = kEqThreads + G * T;       // threads that take part in the named barriers
-    // Warp placement.  A warp's scheduler partition is (warp id mod 4) and an EQ warp carries about four times the
+    // Warp placement.  A warp's scheduler partition is (warp id mod 4) and an EQ warp carries three to four times the
     // instructions of a convolution warp, so the roles are spread to equalise the partitions' load: EQ warp w sits on
     // partition w (warp id w); each convolution warp goes to the least-loaded partition; unused warp slots exit at
     // once.  (Config 2, G = 7: partitions 0-2 hold one EQ + one convolution warp, partition 3 four convolution warps.)
@@ -365,20 +370,22 @@ template <int N, int G>
 __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned char* smem, int stream0, int w) {
     using SM = RenderSmem<N, G>;
     constexpr int B = SM::B;
-    constexpr int DL = kEqSkew;                        // lane skew in steps = steps per unrolled iteration
+    constexpr int DL = (B >= 128) ? kEqSkew : 4;       // lane skew in steps = steps per unrolled iteration
     constexpr int NQ = DL / 4;                         // float4 input loads per iteration
-    constexpr int kOutLag = DL * (kEqGroup - 1) + 1;   // steps the last band runs behind the first (33)
-    constexpr int kGrp = kOutLag + 3;                  // the group stored at local step i is samples [i-kGrp, i-kGrp+3]
-    constexpr int kLagA = (kGrp + DL - 1) / DL * DL;   // steps of a block during which the previous block is still being finished
-    static_assert((DL == 4 || DL == 8) && kEqGroup == 5 && kGrp % 4 == 0 && B % DL == 0 && B >= kLagA, "systolic loop layout");
+    constexpr int BPL = kEqBandsPerLane;
+    constexpr int kOutLag = DL * (kEqGroup - 1) + (BPL - 1);  // steps the last band runs behind the first
+    constexpr int kStoreU = (kOutLag + 3) % 4;         // the last lane completes an aligned group of 4 samples when u % 4 == kStoreU
+    constexpr int kLagA = (kOutLag + DL - 1) / DL * DL;  // steps of a block during which the previous block is still being finished
+    constexpr int kPending = 3 - kStoreU;              // outputs computed after the last group store of an iteration
+    static_assert((DL == 4 || DL == 8) && BPL == 2 && B % DL == 0 && B >= kLagA, "systolic loop layout");
     constexpr int kCount = SM::kWorkers;
     float* ring_f = reinterpret_cast<float*>(smem + SM::kRingOff);
     float* stage = reinterpret_cast<float*>(smem + SM::kStageOff);
 
     const int lane = threadIdx.x & 31;
-    const int c_raw = 6 * w + lane / kEqGroup;           // chain index in the CTA: 2*stream + channel
+    const int c_raw = kEqChainsPerWarp * w + lane / kEqGroup;  // chain index in the CTA: 2*stream + channel
     const int l = lane % kEqGroup;
-    const bool chain_ok = (lane < 6 * kEqGroup) && (c_raw < 2 * G);
+    const bool chain_ok = (lane < kEqChainsPerWarp * kEqGroup) && (c_raw < 2 * G);
     const int c = chain_ok ? c_raw : 0;
     const int g = c >> 1, ch = c & 1;
     const int s = stream0 + g;
@@ -389,17 +396,18 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     float ab0 = 0.f, ab1 = 0.f, ab2 = 0.f, aa1 = 0.f, aa2 = 0.f, as1 = 0.f, as2 = 0.f;
     float bb0 = 0.f, bb1 = 0.f, bb2 = 0.f, ba1 = 0.f, ba2 = 0.f, bs1 = 0.f, bs2 = 0.f;
     bool en_a = false, en_b = false;
-    const bool has_a = lane_valid && do_eq && (2 * l) < p.n_bands, has_b = lane_valid && do_eq && (2 * l + 1) < p.n_bands;
+    const int band_a = BPL * l, band_b = BPL * l + 1;
+    const bool has_a = lane_valid && do_eq && band_a < p.n_bands, has_b = lane_valid && do_eq && band_b < p.n_bands;
     if (has_a) {
-        const float* cf = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + 2 * l) * kEqCoefStride;
+        const float* cf = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + band_a) * kEqCoefStride;
         ab0 = cf[0]; ab1 = cf[1]; ab2 = cf[2]; aa1 = cf[3]; aa2 = cf[4]; en_a = cf[5] != 0.f;
-        const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + 2 * l);
+        const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + band_a);
         as1 = st[ch]; as2 = st[2 + ch];
     }
     if (has_b) {
-        const float* cf = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + 2 * l + 1) * kEqCoefStride;
+        const float* cf = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + band_b) * kEqCoefStride;
         bb0 = cf[0]; bb1 = cf[1]; bb2 = cf[2]; ba1 = cf[3]; ba2 = cf[4]; en_b = cf[5] != 0.f;
-        const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + 2 * l + 1);
+        const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + band_b);
         bs1 = st[ch]; bs2 = st[2 + ch];
     }
 
@@ -441,7 +449,6 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
 
     const int src_lane = (l == 0) ? lane : lane - 1;
     const bool first = (l == 0), last = (l == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
-    const unsigned zmask = p.zero_mask;
     float xs[DL], yl[DL];  // xs: band-A inputs of the next DL steps, shuffled over from lane l-1;  yl: last DL band-B outputs
 #pragma unroll
     for (int u = 0; u < DL; ++u) { xs[u] = 0.f; yl[u] = 0.f; }
@@ -456,20 +463,16 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     auto fast_iter = [&](const In& in, int i0, float* dprev_end, float* dcur) {
 #pragma unroll
         for (int u = 0; u < DL; ++u) {
-            // xs[u] was shuffled over DL-1 steps ago.  Left alone, ptxas hoists this select to ~23 instructions after
-            // the SHFL and the warp then stalls on the shuffle's real (contended) latency; OR-ing in (previous output &
-            // run-time 0) keeps the value bit-identical but pins its first use to this step.
-            const float xr = __uint_as_float(__float_as_uint(xs[u]) | (__float_as_uint(ya_prev) & zmask));
-            const float xa = first ? in_at(in, u) : xr;
-            const float yb = df2t_step(ya_prev, bs1, bs2, bb0, bb1, bb2, ba1, ba2);
+            const float xa = first ? in_at(in, u) : xs[u];  // shuffled over DL-1 steps ago
+            const float y = df2t_step(ya_prev, bs1, bs2, bb0, bb1, bb2, ba1, ba2);   // band B on band A's previous output
             ya_prev = df2t_step(xa, as1, as2, ab0, ab1, ab2, aa1, aa2);
-            xs[(u + DL - 1) % DL] = __shfl_sync(0xffffffffu, yb, src_lane);
-            if ((u & 3) == 0 && last) {
-                const int g0 = i0 + u - kGrp;
+            xs[(u + DL - 1) % DL] = __shfl_sync(0xffffffffu, y, src_lane);
+            if ((u & 3) == kStoreU && last) {
+                const int g0 = i0 + u - 3 - kOutLag;
                 float* dstp = (g0 < 0 ? dprev_end : dcur) + g0;
-                *reinterpret_cast<float4*>(dstp) = make_float4(yl[(u + DL - 3) % DL], yl[(u + DL - 2) % DL], yl[(u + DL - 1) % DL], yb);
+                *reinterpret_cast<float4*>(dstp) = make_float4(yl[(u + DL - 3) % DL], yl[(u + DL - 2) % DL], yl[(u + DL - 1) % DL], y);
             }
-            yl[u] = yb;
+            yl[u] = y;
         }
     };
     // DL checked steps (pipeline fill and drain, ragged blocks, disabled bands): state and outputs are committed only
@@ -483,18 +486,18 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             const bool act_a = lane_valid && na >= 0 && na < nb, act_b = lane_valid && nbi >= 0 && nbi < nb;
             const float xa = first ? in_at(in, u) : xs[u];
             float t1 = bs1, t2 = bs2;
-            float yb = df2t_step(ya_prev, t1, t2, bb0, bb1, bb2, ba1, ba2);
+            float y = df2t_step(ya_prev, t1, t2, bb0, bb1, bb2, ba1, ba2);
             const bool upd_b = act_b && en_b;
             bs1 = upd_b ? t1 : bs1; bs2 = upd_b ? t2 : bs2;
-            yb = upd_b ? yb : ya_prev;
+            y = upd_b ? y : ya_prev;
             t1 = as1; t2 = as2;
             float ya = df2t_step(xa, t1, t2, ab0, ab1, ab2, aa1, aa2);
             const bool upd_a = act_a && en_a;
             as1 = upd_a ? t1 : as1; as2 = upd_a ? t2 : as2;
             ya_prev = upd_a ? ya : xa;
-            xs[(u + DL - 1) % DL] = __shfl_sync(0xffffffffu, yb, src_lane);
-            if (act_b && last) dst0[nbi] = yb;
-            yl[u] = yb;
+            xs[(u + DL - 1) % DL] = __shfl_sync(0xffffffffu, y, src_lane);
+            if (act_b && last) dst0[nbi] = y;
+            yl[u] = y;
         }
     };
     // input samples [i, i+DL) of a staged row (zeros past the end of the block)
@@ -521,7 +524,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
 
     // Every valid band filters and the launch is whole blocks: the chain runs continuously across the launch's blocks,
     // filling once at the start and draining once at the end.
-    const bool lane_fast = !lane_valid || !do_eq || (en_a && en_b && has_a && has_b);
+    const bool lane_fast = !lane_valid || !do_eq || (en_a && has_a && en_b && has_b);
     const bool all_fast = __all_sync(0xffffffffu, lane_fast);
     const bool continuous = do_eq && p.tail_frames == B && (SM::kEqWarps > 1 ? __syncthreads_and_eq<SM::kEqThreads>(all_fast) : all_fast);
     float* ring_c = ring_f + (size_t)g * SM::kRingStride + ch * B;  // this chain's channel row of slot 0 (slots are 2*B apart)
@@ -550,7 +553,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             float* dl = ring_c + ((p.n_blocks - 1) % 3) * 2 * B;
             if (last) {
 #pragma unroll
-                for (int e = 0; e < 3; ++e) dl[B - 1 - kOutLag - 2 + e] = yl[DL - 3 + e];
+                for (int e = 0; e < kPending; ++e) dl[B - kOutLag - kPending + e] = yl[DL - kPending + e];
             }
             In zero;
 #pragma unroll
@@ -587,8 +590,8 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             bar_arrive(kBarFull0 + (t & 1), kCount);
         }
     }
-    if (has_a) { float* st = reinterpret_cast<float*>(p.eqs + (size_t)s * kMaxBands + 2 * l); st[ch] = as1; st[2 + ch] = as2; }
-    if (has_b) { float* st = reinterpret_cast<float*>(p.eqs + (size_t)s * kMaxBands + 2 * l + 1); st[ch] = bs1; st[2 + ch] = bs2; }
+    if (has_a) { float* st = reinterpret_cast<float*>(p.eqs + (size_t)s * kMaxBands + band_a); st[ch] = as1; st[2 + ch] = as2; }
+    if (has_b) { float* st = reinterpret_cast<float*>(p.eqs + (size_t)s * kMaxBands + band_b); st[ch] = bs1; st[2 + ch] = bs2; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
