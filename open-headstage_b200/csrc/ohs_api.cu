@@ -323,10 +323,11 @@ int pick_streams_per_cta(const ohs_engine* h) {
     cudaDeviceProp prop{};
     int sms = 148;
     if (cudaGetDeviceProperties(&prop, h->cfg.device) == cudaSuccess) sms = prop.multiProcessorCount;
-    // spread the streams evenly over the SMs: ceil(n_streams / SMs) per CTA (config 2: 1024 streams -> 7 per CTA, 147
-    // CTAs), capped by what fits in one CTA
+    // Few streams per SM (config 2: 1024 streams -> 7 per CTA, 147 CTAs): one CTA per SM holding ceil(n_streams / SMs)
+    // streams, so every SM gets the same share.  Many streams per SM (config 3: 55 per SM): CTAs of three streams, whose
+    // six chains exactly fill one EQ warp, several CTAs resident per SM (measured best on config 3).
     int g = (h->cfg.n_streams + sms - 1) / sms;
-    g = std::max(1, std::min(g, kMaxG));
+    g = (g > kMaxG) ? 3 : std::max(1, g);
     while (g > 1 && !render_fits(h->N, g)) --g;
     return g;
 }

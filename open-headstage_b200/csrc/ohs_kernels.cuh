@@ -301,8 +301,17 @@ template <int N, int G> struct RenderSmem {
         int conv_warp_id[kConvWarps > 0 ? kConvWarps : 1];
         int total_warps;
     };
+    // Balancing pads the CTA with idle warp slots, which only pays when one CTA owns the SM (N >= 512: config 2 and the
+    // long-BRIR config); smaller transforms run several CTAs per SM, which balances the partitions by itself, and
+    // there the roles are packed densely.
+    static constexpr bool kBalanced = (N >= 512);
     static constexpr Placement place() {
         Placement pl{};
+        if (!kBalanced) {
+            for (int f = 0; f < kConvWarps; ++f) pl.conv_warp_id[f] = kEqWarps + f;
+            pl.total_warps = kEqWarps + kConvWarps;
+            return pl;
+        }
         int load[4] = {0, 0, 0, 0}, count[4] = {0, 0, 0, 0};
         for (int w = 0; w < kEqWarps; ++w) { load[w & 3] += 4; count[w & 3] += 1; }
         for (int f = 0; f < kConvWarps; ++f) {
@@ -332,7 +341,7 @@ template <int N, int G> struct RenderSmem {
     static constexpr bool kFits = kBytes <= 227 * 1024 && kThreads <= 1024;
     // Register budget.  Warps are allocated in groups of four; as many CTAs per SM as shared memory allows (up to
     // four) while every thread keeps at least 80 registers.
-    static constexpr int kWarpsAlloc = kThreads / 32;  // already a multiple of four
+    static constexpr int kWarpsAlloc = (kThreads / 32 + 3) / 4 * 4;
     static constexpr int kBySmem = (int)((227 * 1024) / (kBytes + 1024));
     static constexpr int kByRegs = 65536 / (80 * 32 * kWarpsAlloc);
     static constexpr int kMinBlocks0 = kBySmem < kByRegs ? kBySmem : kByRegs;
