@@ -677,7 +677,67 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     float* out_r = out_l + p.row_stride;
     auto stream_sync = [&]() { if (T > 32) bar_sync(kBarStream0 + g, T); else __syncwarp(); };
 
+    constexpr int kPairs = N / 4 / T;
+    // one delay-line partition's worth of operands of a bin pair: Z[k], Z[k+1], Z[mirror k], Z[mirror k+1] and their filters
+    struct Operands { float4 uu; float2 v0, v1; float4 f0, f1, g0, g1; };
+    auto load_ops = [&](const float2* zq, const float4* fq, int k, int m0, int m1) {
+        Operands o;
+        o.uu = *reinterpret_cast<const float4*>(zq + k);
+        o.v0 = zq[m0]; o.v1 = zq[m1];
+        o.f0 = fq[k]; o.f1 = fq[k + 1]; o.g0 = fq[m0]; o.g1 = fq[m1];
+        return o;
+    };
+    auto mac_ops = [&](float2 (&acc)[4], const Operands& o, int k) {
+        const float2 u0 = make_float2(o.uu.x, o.uu.y), u1 = make_float2(o.uu.z, o.uu.w);
+        mac_bin(acc[0], u0, k ? o.v0 : u0, o.f0);
+        mac_bin(acc[1], u1, o.v1, o.f1);
+        mac_bin(acc[2], o.v0, k ? u0 : o.v0, o.g0);
+        mac_bin(acc[3], o.v1, u1, o.g1);
+    };
+
     for (int t = 0; t < p.n_blocks; ++t) {
+        int slot = p.head + t;
+        slot -= (slot / p.pmax) * p.pmax;
+        // ---- delay-line history first.  The partitions 1..P-1 of this block's product only need spectra of EARLIER
+        // blocks, so their multiply-accumulate (the HBM-heavy part of a long impulse response: P-1 tiles of 8*N bytes per
+        // stream) runs BEFORE the wait for this block's EQ output and overlaps the EQ warps' sequential work.  A thread
+        // owns adjacent bins (k, k+1), k even, k < N/2, and their mirror bins N-k, N-k-1 (bin 0 pairs with itself, N/2
+        // rides along with it); four partitions' operands are in flight at once.
+        float2 acc[kPairs][4];  // W[k], W[k+1], W[mirror(k)], W[mirror(k+1)]
+#pragma unroll
+        for (int m = 0; m < kPairs; ++m)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[m][e] = make_float2(0.f, 0.f);
+        if (valid && p.conv_enable && nparts > 1) {
+#pragma unroll 1
+            for (int m = 0; m < kPairs; ++m) {
+                const int k = 2 * (tid + m * T);
+                const int m0 = k ? N - k : N / 2, m1 = N - k - 1;
+                float2 a4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+                int q = 1;
+#pragma unroll 1
+                for (; q + 3 < nparts; q += 4) {
+                    Operands o[4];
+#pragma unroll
+                    for (int jq = 0; jq < 4; ++jq) {
+                        int sl = slot - (q + jq); if (sl < 0) sl += p.pmax;
+                        o[jq] = load_ops(fdl_s + (size_t)sl * N, filt + (size_t)(q + jq) * N, k, m0, m1);
+                    }
+#pragma unroll
+                    for (int jq = 0; jq < 4; ++jq) mac_ops(a4, o[jq], k);
+                }
+#pragma unroll 1
+                for (; q < nparts; ++q) {
+                    int sl = slot - q; if (sl < 0) sl += p.pmax;
+                    const Operands o = load_ops(fdl_s + (size_t)sl * N, filt + (size_t)q * N, k, m0, m1);
+                    mac_ops(a4, o, k);
+                }
+                // scatter back into the per-pair accumulators with static indices
+#pragma unroll
+                for (int mm = 0; mm < kPairs; ++mm)
+                    if (mm == m) { acc[mm][0] = a4[0]; acc[mm][1] = a4[1]; acc[mm][2] = a4[2]; acc[mm][3] = a4[3]; }
+            }
+        }
         bar_sync(kBarFull0 + (t & 1), kCount);
         const int cur = t % 3, prv = (t + 2) % 3;
         const float* xc = ring_g + cur * 2 * B;
@@ -701,10 +761,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
         fft_run<N, T>(tid, tw, b0, b1, RingWindow{xp, xc, B}, zbuf, stream_sync,
                       [&]() { if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount); });
         stream_sync();
-        // ---- frequency-domain delay line + 4-path multiply-accumulate.  A thread owns adjacent bins (k, k+1), k even,
-        // k < N/2, and their mirror bins N-k, N-k-1 (bin 0 pairs with itself, and N/2 rides along with it).
-        int slot = p.head + t;
-        slot -= (slot / p.pmax) * p.pmax;
+        // ---- this block's spectrum: into the delay line, and its product with partition 0 on top of the history
         if (nparts > 1) {
             float4* dstz = reinterpret_cast<float4*>(fdl_s + (size_t)slot * N);
 #pragma unroll
@@ -715,45 +772,17 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
                 dstz[i >> 1] = make_float4(z0.x, z0.y, z1.x, z1.y);
             }
         }
-        constexpr int kPairs = N / 4 / T;
-        float2 acc[kPairs][4];  // W[k], W[k+1], W[mirror(k)], W[mirror(k+1)]
 #pragma unroll
         for (int m = 0; m < kPairs; ++m) {
             const int k = 2 * (tid + m * T);
             const int m0 = k ? N - k : N / 2, m1 = N - k - 1;
+            Operands o;
             float2 u0, u1;
             zbuf.ld2(k, u0, u1);
-            const float2 v0 = zbuf.ld(m0), v1 = zbuf.ld(m1);
-            const float4 f0 = filt[k], f1 = filt[k + 1], g0 = filt[m0], g1 = filt[m1];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[m][e] = make_float2(0.f, 0.f);
-            mac_bin(acc[m][0], u0, k ? v0 : u0, f0);
-            mac_bin(acc[m][1], u1, v1, f1);
-            mac_bin(acc[m][2], v0, k ? u0 : v0, g0);
-            mac_bin(acc[m][3], v1, u1, g1);
-        }
-        for (int q = 1; q < nparts; ++q) {
-            int sl = slot - q; if (sl < 0) sl += p.pmax;
-            const float2* zq = fdl_s + (size_t)sl * N;
-            const float4* fq = filt + (size_t)q * N;
-#pragma unroll
-            for (int m = 0; m < kPairs; ++m) {
-                const int k = 2 * (tid + m * T);
-                const int m0 = k ? N - k : N / 2, m1 = N - k - 1;
-                const float4 uu = *reinterpret_cast<const float4*>(zq + k);
-                const float2 u0 = make_float2(uu.x, uu.y), u1 = make_float2(uu.z, uu.w);
-                const float2 v0 = zq[m0], v1 = zq[m1];
-                const float4 f0 = fq[k], f1 = fq[k + 1], g0 = fq[m0], g1 = fq[m1];
-                mac_bin(acc[m][0], u0, k ? v0 : u0, f0);
-                mac_bin(acc[m][1], u1, v1, f1);
-                mac_bin(acc[m][2], v0, k ? u0 : v0, g0);
-                mac_bin(acc[m][3], v1, u1, g1);
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < kPairs; ++m) {
-            const int k = 2 * (tid + m * T);
-            const int m0 = k ? N - k : N / 2, m1 = N - k - 1;
+            o.uu = make_float4(u0.x, u0.y, u1.x, u1.y);
+            o.v0 = zbuf.ld(m0); o.v1 = zbuf.ld(m1);
+            o.f0 = filt[k]; o.f1 = filt[k + 1]; o.g0 = filt[m0]; o.g1 = filt[m1];
+            mac_ops(acc[m], o, k);
             // swap(re, im): the inverse transform is run as swap(FFT(swap(W)))
             wbuf.st2(k, make_float2(acc[m][0].y, acc[m][0].x), make_float2(acc[m][1].y, acc[m][1].x));
             wbuf.st(m0, make_float2(acc[m][2].y, acc[m][2].x));
