@@ -6,22 +6,25 @@
 // i.e. the work of reference src/lib.rs:1179-1207 (Plugin::process) over src/dsp/parametric_eq.rs:166-179 and
 // src/dsp/convolution.rs:184-289, for many streams at once.
 //
-// Design (see DESIGN.md for the derivations and the measured pipe numbers behind them):
-//   * warp 0 of the CTA is the EQ warp: band-systolic — lane (g, j) runs band j of stream g, two samples behind lane
-//     (g, j-1), passing the stereo sample down the lanes by shuffle.  Every band's recurrence stays strictly sequential
-//     in the reference's operation order; left and right share the coefficients and ride in one packed f32x2 register
-//     (FMUL2 / FFMA2 with a run-time 1.0 multiplier — ptxas 12.9 contracts mul.f32x2+add.f32x2 into FFMA2 even under
-//     -fmad=false, which would break bit parity; an FFMA2 by an opaque 1.0 cannot be contracted and rounds once).
-//     The warp also stages the next block's input rows into shared memory (cp.async, 16 B) while it filters.
-//   * the other warps are the convolution warps, T = max(32, N/8) threads per stream: left + i*right go through ONE
-//     complex N = 2B point Stockham FFT in shared memory (radix 8/4/2 in registers), the frequency-domain delay line
-//     keeps that packed spectrum Z, and the four HRIR paths are applied as
+// Design (DESIGN.md §4 has the derivations, the measured pipe numbers and the ncu evidence behind each choice):
+//   * EQ warps: band-systolic in time.  Lane (c, l) owns bands 2l and 2l+1 of chain c = (stream, channel); at step s
+//     band A filters sample s-8l with the input shuffled over from lane l-1 seven steps earlier, band B filters sample
+//     s-8l-1 with band A's previous output.  Every band's recurrence stays strictly sequential in the reference's
+//     operation order with explicitly rounded, never-contracted scalar ops: bit-exact.  (Packed f32x2 was measured
+//     slower, and ptxas 12.9 contracts mul.f32x2+add.f32x2 into FFMA2 even under -fmad=false.)  The chain runs
+//     continuously across the blocks of a launch.  The same warps stage the next block's input rows into shared memory
+//     (cp.async, 16 B) one block ahead.
+//   * convolution warps, T = max(32, N/16) threads per stream (one warp at N = 512): left + i*right go through ONE
+//     complex N = 2B point Stockham FFT in shared memory (radix 8/4/2 in registers, two adjacent butterflies per thread
+//     so every shared-memory access is 128-bit), the frequency-domain delay line keeps that packed spectrum Z, and the
+//     four HRIR paths are applied as
 //         W[k] = sum_p  Z_{t-p}[k] * A_p[k] + conj(Z_{t-p}[N-k]) * C_p[k]
 //     with A = (G_L - i G_R)/2N, C = (G_L + i G_R)/2N, G_L = FFT(h_LSL + i h_LSR), G_R = FFT(h_RSL + i h_RSR):
 //     Re IFFT(W) is the left ear (LSL + RSL), Im IFFT(W) the right ear (LSR + RSR) (src/dsp/convolution.rs:229-230).
-//     One forward and one inverse FFT per block instead of the reference's four and four.
+//     One forward and one inverse FFT per block instead of the reference's four and four.  The products with the
+//     delay line's OLDER spectra (partitions 1..P-1) are accumulated before the wait for the block's EQ output.
 //   * the two roles are decoupled by named barriers over a 3-slot ring of filtered blocks, so the EQ of block t+1
-//     overlaps the convolution of block t.
+//     overlaps the convolution of block t, and are placed on the four scheduler partitions so that their loads balance.
 #pragma once
 
 #include <cuda_runtime.h>
