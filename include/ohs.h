@@ -149,6 +149,14 @@ int ohs_launch_count(ohs_engine* h, uint64_t* out);
 /* Elapsed device time (ms) of the render kernels of the most recent ohs_process_device call; blocks until done. */
 int ohs_last_kernel_ms(ohs_engine* h, float* ms);
 
+/* Object mixdown (BASELINE config 4; an extension — the reference has no multi-source mode): sums the rendered
+ * streams of this engine into one stereo bus, d_bus[c * bus_stride + n] = sum_s d_in[(s*2 + c) * row_stride + n].
+ * Two mono sources ride in one stereo stream: source A as the left input with paths (LSL, LSR) = its (left-ear,
+ * right-ear) HRIRs, source B as the right input with (RSL, RSR); the engine's output is already their binaural mix
+ * (src/dsp/convolution.rs:229-230).  n_frames must be a multiple of 4; pointers 16-byte aligned.  Enqueues on the
+ * engine's stream.  The per-GPU buses are then summed with NCCL (parallel.reduce_bus). */
+int ohs_mix_device(ohs_engine* h, const float* d_in, float* d_bus, size_t n_frames, size_t row_stride, size_t bus_stride);
+
 /* pinned host memory helpers */
 int ohs_host_alloc(void** p, size_t bytes);
 int ohs_host_free(void* p);

@@ -5,7 +5,7 @@ The compute path is the hand-written CUDA in csrc/ behind the C ABI of include/o
 by _build.build_library()).  This package is the thin host side: a ctypes binding, Python mirrors of the
 reference's `ConvolutionEngine` / `StereoParametricEQ`, and the seeded synthetic inputs of the BASELINE configs.
 """
-from . import parallel, signals  # noqa: F401
+from . import autoeq, parallel, signals, sofa  # noqa: F401
 from ._build import build_host_tests, build_library  # noqa: F401
 from .engine import (  # noqa: F401
     ALLPASS, BANDPASS, HIGHPASS, HIGHSHELF, LOWPASS, LOWSHELF, LSL, LSR, NOTCH, OHS_ALL, PEAK, RSL, RSR, SYMBOLS,

@@ -691,6 +691,22 @@ int ohs_last_kernel_ms(ohs_engine* h, float* ms) {
     return OHS_OK;
 }
 
+int ohs_mix_device(ohs_engine* h, const float* d_in, float* d_bus, size_t n_frames, size_t row_stride, size_t bus_stride) {
+    OHS_CHECK_HANDLE(h);
+    if (!d_in || !d_bus) return fail(OHS_ERR_INVALID, "null audio pointer");
+    if (n_frames % 4 || row_stride % 4 || bus_stride % 4 || (((uintptr_t)d_in | (uintptr_t)d_bus) & 15u))
+        return fail(OHS_ERR_ALIGNMENT, "mixdown needs 16-byte aligned pointers and frame counts / strides that are multiples of 4");
+    if (row_stride < n_frames || bus_stride < n_frames) return fail(OHS_ERR_INVALID, "stride smaller than n_frames");
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    if (n_frames == 0) return OHS_OK;
+    const unsigned threads = 256;
+    dim3 grid((unsigned)((n_frames / 4 + threads - 1) / threads), 2);
+    mix_streams_kernel<<<grid, threads, 0, h->stream>>>(d_in, d_bus, h->cfg.n_streams, n_frames, row_stride, bus_stride);
+    OHS_CUDA(cudaGetLastError());
+    h->launches++;
+    return OHS_OK;
+}
+
 int ohs_host_alloc(void** p, size_t bytes) {
     if (!p) return fail(OHS_ERR_INVALID, "null output");
     OHS_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));

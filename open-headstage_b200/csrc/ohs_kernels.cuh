@@ -908,4 +908,21 @@ __global__ void clear_history_kernel(float2* fdl, float2* prev, const int* strea
     for (size_t i = threadIdx.x; i < prev_per_stream; i += blockDim.x) q[i] = make_float2(0.f, 0.f);
 }
 
+// Object mixdown (BASELINE config 4): bus[c][n] = sum over streams of in[s][c][n].  Sequential f32 sum in stream order
+// (deterministic); one thread per four frames, rows read with coalesced 16-byte loads.
+__global__ void mix_streams_kernel(const float* __restrict__ in, float* __restrict__ bus, int n_streams, size_t n_frames,
+                                   size_t row_stride, size_t bus_stride) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index inside a row
+    const int c = blockIdx.y;
+    if (q * 4 >= n_frames) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* row = in + (size_t)c * row_stride + q * 4;
+#pragma unroll 4
+    for (int s = 0; s < n_streams; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(row + (size_t)s * 2 * row_stride);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(bus + (size_t)c * bus_stride + q * 4) = acc;
+}
+
 }  // namespace ohs

@@ -64,6 +64,7 @@ SYMBOLS = [
     ("ohs_cuda_stream", C.c_int, [_VP, C.POINTER(_VP)]),
     ("ohs_launch_count", C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     ("ohs_last_kernel_ms", C.c_int, [_VP, C.POINTER(C.c_float)]),
+    ("ohs_mix_device", C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_size_t, C.c_size_t]),
     ("ohs_host_alloc", C.c_int, [C.POINTER(_VP), C.c_size_t]),
     ("ohs_host_free", C.c_int, [_VP]),
     ("ohs_state_bytes", C.c_int, [_VP, C.POINTER(C.c_size_t)]),
@@ -246,6 +247,11 @@ class Engine:
     def process_device(self, d_in: int, d_out: int, n_frames: int, row_stride: int | None = None):
         """Device flavour: raw device pointers (e.g. torch.Tensor.data_ptr()); enqueues on the engine's stream."""
         _check(self._L.ohs_process_device(self._h, d_in, d_out, n_frames, n_frames if row_stride is None else row_stride))
+
+    def mix_device(self, d_in: int, d_bus: int, n_frames: int, row_stride: int | None = None, bus_stride: int | None = None):
+        """Sum this engine's rendered streams into a stereo bus [2][bus_stride] (config 4 object mixdown)."""
+        _check(self._L.ohs_mix_device(self._h, d_in, d_bus, n_frames, n_frames if row_stride is None else row_stride,
+                                      n_frames if bus_stride is None else bus_stride))
 
     def sync(self):
         _check(self._L.ohs_sync(self._h))

@@ -60,3 +60,48 @@ def reduce_bus(bus: torch.Tensor, dst: int = 0, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.reduce(bus, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return bus
+
+
+def render_object_mix(pkg, sources, hrirs, block: int, fs: float, eq_preset=None, gain: float = 1.0, device: int = 0,
+                      src: int = 0, group=None):
+    """BASELINE config 4 on this rank's share: `sources` [n_src, n_frames] mono signals (n_src even), `hrirs`
+    [n_src, 2, taps] (left-ear, right-ear impulse responses of each source's direction).  Two sources ride in one stereo
+    stream of the engine (source 2i on the left input with paths LSL/LSR, source 2i+1 on the right input with RSL/RSR);
+    the rendered streams are summed into this rank's stereo bus on the GPU, the buses are summed onto rank `src` with
+    NCCL, and the EQ and the output gain are applied ONCE to the reduced bus there (the definition of SURVEY.md §8e —
+    the reference has no multi-source mode).  Returns the [2, n_frames] bus (torch, CUDA) on `src`, None elsewhere."""
+    import numpy as np
+
+    n_src, n_frames = sources.shape
+    assert n_src % 2 == 0 and n_frames % block == 0 and n_frames % 4 == 0
+    taps = hrirs.shape[2]
+    n_streams = n_src // 2
+    eng = pkg.Engine(n_streams, block, taps, n_bands=0, n_hrir_sets=n_streams, device=device, sample_rate=fs)
+    for i in range(n_streams):
+        eng.set_ir(0, hrirs[2 * i, 0], hrir_set=i)      # LSL: source 2i   -> left ear
+        eng.set_ir(1, hrirs[2 * i, 1], hrir_set=i)      # LSR: source 2i   -> right ear
+        eng.set_ir(2, hrirs[2 * i + 1, 0], hrir_set=i)  # RSL: source 2i+1 -> left ear
+        eng.set_ir(3, hrirs[2 * i + 1, 1], hrir_set=i)  # RSR: source 2i+1 -> right ear
+        eng.bind_stream_hrir(i, i)
+    x = torch.from_numpy(np.ascontiguousarray(sources.reshape(n_streams, 2, n_frames), dtype=np.float32)).to("cuda:%d" % device)
+    y = torch.empty_like(x)
+    bus = torch.zeros((2, n_frames), dtype=torch.float32, device=x.device)
+    torch.cuda.synchronize(x.device)
+    eng.process_device(x.data_ptr(), y.data_ptr(), n_frames)
+    eng.mix_device(y.data_ptr(), bus.data_ptr(), n_frames)
+    eng.sync()
+    reduce_bus(bus, dst=src, group=group)
+    rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+    if rank != src:
+        return None
+    if eq_preset is not None or gain != 1.0:
+        post = pkg.Engine(1, block, 1, n_bands=10, device=device, sample_rate=fs)
+        post.set_conv_enable(False)
+        if eq_preset is not None:
+            post.eq_set_preset(eq_preset)
+            post.set_eq_enable(True)
+        post.set_gain(gain)
+        torch.cuda.synchronize(x.device)
+        post.process_device(bus.data_ptr(), bus.data_ptr(), n_frames)
+        post.sync()
+    return bus

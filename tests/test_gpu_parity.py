@@ -427,3 +427,33 @@ def test_cpp_mirror_replays_reference_unit_tests():
     r = subprocess.run([binary], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "PASSED" in r.stdout and "FAIL" not in r.stdout
+
+
+def test_config4_object_mixdown(cipic):
+    """BASELINE config 4 in miniature (one rank): 24 mono sources, each with its own direction from the bundled CIPIC set
+    (idx = source*37 mod 1250), mixed to one stereo bus, EQ + gain applied once on the bus.  Config 4 has no reference
+    behaviour (the reference has no multi-source mode); the definition is checked against an f64 evaluation."""
+    import torch
+    from open_headstage_b200 import parallel as P
+
+    n_src, block, n = 24, 256, 256 * 12
+    ir = cipic["ir"]
+    hr = np.stack([ir[(s * 37) % 1250] for s in range(n_src)]).astype(np.float32)  # [n_src, 2, 200]
+    src = np.stack([S.pink_noise(n, 4000 + s) for s in range(n_src)]) / np.float32(64.0)
+    bus = P.render_object_mix(ohs, src, hr, block, FS, eq_preset=None, gain=0.5).cpu().numpy()
+    truth = np.zeros((2, n))
+    for s in range(n_src):
+        for ear in range(2):
+            truth[ear] += sps.fftconvolve(src[s].astype(np.float64), hr[s, ear].astype(np.float64))[:n]
+    truth *= 0.5
+    assert np.max(np.abs(bus - truth)) <= TOL
+    assert np.abs(bus).max() > 1e-3
+    # with the bus EQ: compare against the oracle's EQ run on the un-equalised GPU bus (EQ stage is bit-exact)
+    raw = P.render_object_mix(ohs, src, hr, block, FS, eq_preset=None, gain=1.0).cpu().numpy()
+    eqd = P.render_object_mix(ohs, src, hr, block, FS, eq_preset=S.EQ_PRESET_TYPICAL, gain=1.0).cpu().numpy()
+    q = O.StereoParametricEQ(10, FS)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL)
+    for b in range(10):
+        q.set_band_raw(b, coeffs[b], True)
+    l, r = q.process_block(raw[0], raw[1])
+    assert eqd[0].tobytes() == l.tobytes() and eqd[1].tobytes() == r.tobytes()
