@@ -7,7 +7,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB = os.path.join(HERE, "libohs_cuda.so")
+LIB = os.environ.get("OHS_LIB_OVERRIDE") or os.path.join(HERE, "libohs_cuda.so")  # override: A/B experiments only
 SOURCES = [os.path.join(HERE, "csrc", "ohs_api.cu")]
 DEPS = SOURCES + [os.path.join(HERE, "csrc", "ohs_kernels.cuh"), os.path.join(ROOT, "include", "ohs.h")]
 

@@ -108,7 +108,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int NPending> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPending) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// register DFTs (forward, e^{-2 pi i rq/R}), natural order in and out
+// register DFTs (forward, e^{-2 pi i rq/R}), natural order in and out.  Scalar FP32: a packed f32x2 version of the FFT
+// arithmetic (FADD2 complex adds, FMUL2+FFMA2 twiddle products) was measured and is slower here (conv-only 11.1 k vs
+// 8.8 k cycles per block): the packed ops hold the FP32 pipe two cycles, so only issue slots are saved, and those are
+// not what the convolution warps' partition runs out of.
 // ---------------------------------------------------------------------------------------------------------------
 template <int R> struct Dft;
 template <> struct Dft<2> {
