@@ -12,8 +12,8 @@
 //     s-8l-1 with band A's previous output.  Every band's recurrence stays strictly sequential in the reference's
 //     operation order with explicitly rounded, never-contracted scalar ops: bit-exact.  (Packed f32x2 was measured
 //     slower, and ptxas 12.9 contracts mul.f32x2+add.f32x2 into FFMA2 even under -fmad=false.)  The chain runs
-//     continuously across the blocks of a launch.  The same warps stage the next block's input rows into shared memory
-//     (cp.async, 16 B) one block ahead.
+//     continuously across the blocks of a launch.  The next block's input rows are staged HBM -> shared memory by TMA
+//     bulk copies (one per row, completing on an mbarrier), one block ahead.
 //   * convolution warps, T = max(32, N/16) threads per stream (one warp at N = 512): left + i*right go through ONE
 //     complex N = 2B point Stockham FFT in shared memory (radix 8/4/2 in registers, two adjacent butterflies per thread
 //     so every shared-memory access is 128-bit), the frequency-domain delay line keeps that packed spectrum Z, and the
@@ -100,12 +100,27 @@ template <int NT> __device__ __forceinline__ bool __syncthreads_and_eq(bool pred
     return r != 0;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+// ---- TMA (bulk asynchronous copy) + mbarrier: input rows HBM -> shared memory, issued by ONE thread per block of rows
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int NPending> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPending) : "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // register DFTs (forward, e^{-2 pi i rq/R}), natural order in and out.  Scalar FP32: a packed f32x2 version of the FFT
@@ -343,7 +358,8 @@ template <int N, int G> struct RenderSmem {
     // filter spectra of a shared single-set, few-partition HRIR (configs 1-3) are staged here once per launch
     static constexpr size_t kFiltSmemBytes = (N <= 512) ? 16 * 1024 : 0;
     static constexpr size_t kFiltOff = kStageOff + sizeof(float) * 2 * G * kStageStride;
-    static constexpr size_t kBytes = kFiltOff + kFiltSmemBytes;
+    static constexpr size_t kMbarOff = kFiltOff + kFiltSmemBytes;  // uint64_t stage_full[2]
+    static constexpr size_t kBytes = kMbarOff + 16;
     static constexpr bool kFits = kBytes <= 227 * 1024 && kThreads <= 1024;
     // Register budget.  Warps are allocated in groups of four; as many CTAs per SM as shared memory allows (up to
     // four) while every thread keeps at least 80 registers.
@@ -426,23 +442,24 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
         bs1 = st[ch]; bs2 = st[2 + ch];
     }
 
-    // stage loader: rows (g', c') of block t -> stage[t&1][g'][c'][0..B), all EQ warps cooperating
+    // Stage loader: rows (g', c') of block t -> stage[t&1][g'][c'][0..B).  Whole blocks go by TMA: one thread arms the
+    // stage's mbarrier with the byte count and issues one bulk copy per row (B*4 contiguous bytes each); the EQ warps'
+    // critical path carries no copy instructions.  A ragged last block (EQ-only mode) uses plain guarded loads.
+    uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
     auto issue_stage = [&](int t) {
-        constexpr int kChunksPerRow = B / 4;
-        constexpr int kChunks = G * 2 * kChunksPerRow;
         float* dst_base = stage + (size_t)(t & 1) * G * SM::kStageStride;
         const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
         if (nb == B) {
-            for (int q = threadIdx.x; q < kChunks; q += SM::kEqThreads) {
-                const int row = q / kChunksPerRow, off = q - row * kChunksPerRow;
-                const int sg = stream0 + (row >> 1);
-                if (sg < p.n_streams) {
-                    const float* src = p.in + ((size_t)sg * 2 + (row & 1)) * p.row_stride + (size_t)t * B + off * 4;
-                    cp_async16(dst_base + (row >> 1) * SM::kStageStride + (row & 1) * B + off * 4, src);
-                }
+            // lane r of EQ warp 0 copies row r (2G <= 14 rows); lane 0 also arms the barrier.  A copy that completes before
+            // the arming only drives the transaction count negative; the phase still needs lane 0's arrival.
+            const int n_str = (p.n_streams - stream0) < G ? (p.n_streams - stream0) : G;
+            if (threadIdx.x == 0) mbar_expect_tx(&stage_full[t & 1], (unsigned)(n_str * 2 * B * sizeof(float)));
+            const int row = threadIdx.x;
+            if (row < 2 * n_str) {
+                const float* src = p.in + ((size_t)(stream0 + (row >> 1)) * 2 + (row & 1)) * p.row_stride + (size_t)t * B;
+                tma_load_1d(dst_base + (row >> 1) * SM::kStageStride + (row & 1) * B, src, (unsigned)(B * sizeof(float)), &stage_full[t & 1]);
             }
         } else {
-            // ragged last block (EQ-only mode, any host-buffer length): plain guarded loads
             for (int q = threadIdx.x; q < G * 2 * B; q += SM::kEqThreads) {
                 const int row = q / B, n = q - row * B;
                 const int sg = stream0 + (row >> 1);
@@ -451,13 +468,14 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
                         p.in[((size_t)sg * 2 + (row & 1)) * p.row_stride + (size_t)t * B + n];
             }
         }
-        cp_async_commit();
     };
-    // Block t's rows are complete once every EQ warp has waited for its own copies and the EQ warps have met at their
-    // barrier; the same barrier proves that every EQ warp is done reading the other stage buffer (block t-1), so the
-    // copies of block t+1 may start overwriting it.
+    // Block t's rows have landed when the stage's mbarrier completes its (t/2)-th phase.  The EQ warps then meet at
+    // their barrier, which proves that every EQ warp is done reading the other stage buffer (block t-1), so the copies
+    // of block t+1 may start overwriting it (generic-proxy reads ordered before the async-proxy writes by the fence).
     auto wait_stage = [&](int t) {
-        cp_async_wait<0>();
+        const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
+        if (nb == B) mbar_wait(&stage_full[t & 1], (unsigned)((t >> 1) & 1));
+        fence_proxy_async();
         if (SM::kEqWarps > 1) bar_sync(kBarEq, SM::kEqThreads); else __syncwarp();
         if (t + 1 < p.n_blocks) issue_stage(t + 1);
     };
@@ -830,6 +848,12 @@ __global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const Re
             const float2 v = (s < p.n_streams) ? p.prev[(size_t)s * SM::B + n] : make_float2(0.f, 0.f);
             ring[g * SM::kRingStride + 2 * 2 * SM::B + n] = v.x;
             ring[g * SM::kRingStride + 2 * 2 * SM::B + SM::B + n] = v.y;
+        }
+        if (threadIdx.x == 0) {
+            uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
+            mbar_init(&stage_full[0], 1);
+            mbar_init(&stage_full[1], 1);
+            fence_mbar_init();
         }
         if (p.filt_in_smem) {
             // one shared HRIR set with few partitions: its spectra stay in shared memory for the whole launch

@@ -41,7 +41,8 @@ def test_library_is_sm100a_native_code():
     elf = subprocess.run([cuobjdump, "-lelf", lib_path], capture_output=True, text=True).stdout
     assert "sm_100a" in elf
     sass = subprocess.run([cuobjdump, "-sass", lib_path], capture_output=True, text=True).stdout
-    assert "LDGSTS" in sass    # cp.async input staging into shared memory
+    assert "UBLKCP" in sass    # TMA bulk copies (cp.async.bulk) stage the input rows into shared memory
+    assert "SYNCS" in sass     # ... completing on mbarriers
     assert "SHFL.IDX" in sass  # the band-systolic EQ chain
     assert "BAR.ARV" in sass or "BAR.ARRIVE" in sass or "BAR.SYNC" in sass  # named-barrier producer/consumer hand-off
 
