@@ -46,7 +46,7 @@ constexpr int kEqSkew = 8;     // steps between neighbouring lanes of the systol
                                // (~200 cycles) after it was sent, which rides out shared-memory-pipe contention from the FFT warps
 constexpr int kEqCoefStride = 8;  // floats per (eq_set, band): b0 b1 b2 a1 a2 enabled pad pad
 
-enum NamedBarrier { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarEq = 5, kBarStream0 = 6 };
+enum NamedBarrier { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarEq = 5, kBarConv = 6, kBarStream0 = 7 };
 
 struct RenderParams {
     const float* in;            // [stream][2][row_stride]
@@ -71,6 +71,7 @@ struct RenderParams {
     int eq_enable;
     int conv_enable;
     int filt_in_smem;           // 0, or the partition count of the single shared HRIR set staged in shared memory
+    int uniform_set;            // 1 when every stream is bound to HRIR set 0 (enables the TMA filter-tile pipeline)
     float one;                  // 1.0f (kept for ABI stability of the parameter block)
     unsigned zero_mask;         // 0, deliberately opaque to the compiler: pins instruction order in the EQ loop
 };
@@ -358,8 +359,8 @@ template <int N, int G> struct RenderSmem {
     // filter spectra of a shared single-set, few-partition HRIR (configs 1-3) are staged here once per launch
     static constexpr size_t kFiltSmemBytes = (N <= 512) ? 16 * 1024 : 0;
     static constexpr size_t kFiltOff = kStageOff + sizeof(float) * 2 * G * kStageStride;
-    static constexpr size_t kMbarOff = kFiltOff + kFiltSmemBytes;  // uint64_t stage_full[2]
-    static constexpr size_t kBytes = kMbarOff + 16;
+    static constexpr size_t kMbarOff = kFiltOff + kFiltSmemBytes;  // uint64_t stage_full[2], filt_full[2]
+    static constexpr size_t kBytes = kMbarOff + 32;
     static constexpr bool kFits = kBytes <= 227 * 1024 && kThreads <= 1024;
     // Register budget.  Warps are allocated in groups of four; as many CTAs per SM as shared memory allows (up to
     // four) while every thread keeps at least 80 registers.
@@ -702,6 +703,13 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     auto stream_sync = [&]() { if (T > 32) bar_sync(kBarStream0 + g, T); else __syncwarp(); };
 
     constexpr int kPairs = N / 4 / T;
+    // TMA filter-tile pipeline (see the block loop): needs two streams' FFT buffers as tile buffers, one shared set with
+    // more partitions than fit the resident table, and every conv thread of the CTA taking part
+    uint64_t* filt_full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff) + 2;
+    unsigned filt_phase[2] = {0u, 0u};
+    constexpr bool kTmaFilterPath = (G >= 2) && (N >= 1024);  // compiled only where long responses live (register budget)
+    if (kTmaFilterPath && p.uniform_set && !valid) nparts = p.set_parts[0];  // threads of an absent stream still run the tile loop
+    const bool tma_filters = kTmaFilterPath && p.uniform_set && !p.filt_in_smem && p.conv_enable && nparts > 1;
     // one delay-line partition's worth of operands of a bin pair: Z[k], Z[k+1], Z[mirror k], Z[mirror k+1] and their filters
     struct Operands { float4 uu; float2 v0, v1; float4 f0, f1, g0, g1; };
     auto load_ops = [&](const float2* zq, const float4* fq, int k, int m0, int m1) {
@@ -732,7 +740,72 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
         for (int m = 0; m < kPairs; ++m)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[m][e] = make_float2(0.f, 0.f);
-        if (valid && p.conv_enable && nparts > 1) {
+        if constexpr (kTmaFilterPath) { if (tma_filters) {
+            // Long impulse response shared by the CTA's streams (config 5): partition q's filter tile (16*N bytes, the
+            // same for every stream) is brought into shared memory by ONE TMA bulk copy, double-buffered in the FFT
+            // ping-pong buffers of streams 0 and 1 (idle until the forward FFT), while each thread keeps two
+            // partitions' worth of its own delay-line operands in flight in registers.  Partition-outer loop: every
+            // tile is read from L2 once per CTA instead of once per stream, and never through a register prefetch.
+            float4* fbuf[2] = {reinterpret_cast<float4*>(smem + SM::kZOff), reinterpret_cast<float4*>(smem + SM::kZOff) + (size_t)NP};
+            const float4* fsrc = p.filt;  // set 0
+            constexpr unsigned kTileBytes = (unsigned)(sizeof(float4) * N);
+            struct ZOps { float4 uu; float2 v0, v1; };
+            ZOps zr[2][kPairs];
+            auto load_z = [&](ZOps (&dst)[kPairs], int q) {
+                int sl = slot - q; if (sl < 0) sl += p.pmax;
+                const float2* zq = fdl_s + (size_t)sl * N;
+#pragma unroll
+                for (int m = 0; m < kPairs; ++m) {
+                    const int k = 2 * (tid + m * T);
+                    dst[m].uu = *reinterpret_cast<const float4*>(zq + k);
+                    dst[m].v0 = zq[k ? N - k : N / 2];
+                    dst[m].v1 = zq[N - k - 1];
+                }
+            };
+            // the tile buffers were last touched through the generic proxy (previous block's inverse FFT)
+            fence_proxy_async();
+            bar_sync(kBarConv, G * T);
+            if (ft == 0) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (1 + j < nparts) { mbar_expect_tx(&filt_full[j], kTileBytes); tma_load_1d(fbuf[j], fsrc + (size_t)(1 + j) * N, kTileBytes, &filt_full[j]); }
+            }
+            if (valid) {
+                load_z(zr[0], 1);
+                if (2 < nparts) load_z(zr[1], 2);
+            }
+#pragma unroll 1
+            for (int q0 = 1; q0 < nparts; q0 += 2) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int q = q0 + j;
+                    if (q < nparts) {
+                        mbar_wait(&filt_full[j], filt_phase[j]);
+                        filt_phase[j] ^= 1u;
+                        if (valid) {
+                            const float4* fq = fbuf[j];
+#pragma unroll
+                            for (int m = 0; m < kPairs; ++m) {
+                                const int k = 2 * (tid + m * T);
+                                const int m0 = k ? N - k : N / 2, m1 = N - k - 1;
+                                Operands o;
+                                o.uu = zr[j][m].uu; o.v0 = zr[j][m].v0; o.v1 = zr[j][m].v1;
+                                o.f0 = fq[k]; o.f1 = fq[k + 1]; o.g0 = fq[m0]; o.g1 = fq[m1];
+                                mac_ops(acc[m], o, k);
+                            }
+                            if (q + 2 < nparts) load_z(zr[j], q + 2);
+                        }
+                        fence_proxy_async();
+                        bar_sync(kBarConv, G * T);  // every conv thread is done with tile buffer j
+                        if (ft == 0 && q + 2 < nparts) {
+                            mbar_expect_tx(&filt_full[j], kTileBytes);
+                            tma_load_1d(fbuf[j], fsrc + (size_t)(q + 2) * N, kTileBytes, &filt_full[j]);
+                        }
+                    }
+                }
+            }
+        } }
+        if (!tma_filters && valid && p.conv_enable && nparts > 1) {
 #pragma unroll 1
             for (int m = 0; m < kPairs; ++m) {
                 const int k = 2 * (tid + m * T);
@@ -853,6 +926,8 @@ __global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const Re
             uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
             mbar_init(&stage_full[0], 1);
             mbar_init(&stage_full[1], 1);
+            mbar_init(&stage_full[2], 1);  // filt_full[0..1]: filter tiles of the long-impulse-response path
+            mbar_init(&stage_full[3], 1);
             fence_mbar_init();
         }
         if (p.filt_in_smem) {
