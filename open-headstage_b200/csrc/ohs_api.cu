@@ -646,13 +646,11 @@ int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_
     p.eqc = h->d_eqc; p.eqs = h->d_eqs; p.tw = h->d_tw;
     p.pmax = h->pmax; p.head = h->head; p.n_bands = h->cfg.n_bands;
     p.eq_enable = h->eq_enable && h->cfg.n_bands > 0; p.conv_enable = h->conv_enable;
-    p.one = 1.0f;
     p.uniform_set = (h->cfg.n_hrir_sets == 1) ? 1 : 0;
     // one HRIR set shared by every stream and small enough: the kernel keeps its spectra in shared memory
     p.filt_in_smem = 0;
     if (h->cfg.n_hrir_sets == 1 && h->N <= 512 && (size_t)h->h_set_parts[0] * h->N * sizeof(float4) <= 16 * 1024)
         p.filt_in_smem = h->h_set_parts[0];
-    p.zero_mask = 0u;
     OHS_CUDA(cudaEventRecord(h->ev_k0, h->stream));
     rc = launch_render(h, p);
     if (rc) return rc;

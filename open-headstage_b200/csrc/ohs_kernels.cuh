@@ -72,8 +72,6 @@ struct RenderParams {
     int conv_enable;
     int filt_in_smem;           // 0, or the partition count of the single shared HRIR set staged in shared memory
     int uniform_set;            // 1 when every stream is bound to HRIR set 0 (enables the TMA filter-tile pipeline)
-    float one;                  // 1.0f (kept for ABI stability of the parameter block)
-    unsigned zero_mask;         // 0, deliberately opaque to the compiler: pins instruction order in the EQ loop
 };
 
 // ---------------------------------------------------------------------------------------------------------------
