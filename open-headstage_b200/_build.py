@@ -25,16 +25,33 @@ def nvcc_path() -> str:
     return p
 
 
+def _source_hash() -> str:
+    import hashlib
+
+    h = hashlib.sha256()
+    for d in DEPS:
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
+    """The library is current when the hash of its sources (recorded next to it at build time) matches — file times are
+    not trusted: the snapshot that carries the prebuilt .so to the GPU box does not preserve them."""
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    try:
+        with open(LIB + ".srchash") as f:
+            return f.read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if force or is_stale():
-        cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, *SOURCES]
+        tmp = LIB + ".tmp.%d" % os.getpid()
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-o", tmp, *SOURCES]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
@@ -42,7 +59,12 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if verbose or r.returncode:
             print(r.stdout + r.stderr)
         if r.returncode:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
             raise RuntimeError("nvcc failed building libohs_cuda.so")
+        os.replace(tmp, LIB)  # atomic: concurrent ranks never see a half-written library
+        with open(LIB + ".srchash", "w") as f:
+            f.write(_source_hash())
     return LIB
 
 
