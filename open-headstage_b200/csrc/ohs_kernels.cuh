@@ -541,17 +541,22 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
         return in;
     };
     // steady-state iterations covering local steps [i0, i1); inputs are loaded one iteration ahead
-    auto fast_run = [&](const float* row, int i0, int i1, float* dprev_end, float* dcur) {
+    // `signal_after` (a multiple of DL, or -1): once the iteration starting there is done the previous block is complete in
+    // the ring and the convolution warps are released.
+    auto fast_run = [&](const float* row, int i0, int i1, float* dprev_end, float* dcur, int signal_after, int full_id) {
+        auto signal = [&]() { __threadfence_block(); bar_arrive(full_id, kCount); };
         In a = ld_in(row, i0), b;
         int i = i0;
 #pragma unroll 1
         for (; i + 2 * DL <= i1; i += 2 * DL) {
             b = ld_in(row, i + DL);
             fast_iter(a, i, dprev_end, dcur);
+            if (i == signal_after) signal();
             a = ld_in(row, i + 2 * DL);
             fast_iter(b, i + DL, dprev_end, dcur);
+            if (i + DL == signal_after) signal();
         }
-        if (i < i1) fast_iter(a, i, dprev_end, dcur);
+        if (i < i1) { fast_iter(a, i, dprev_end, dcur); if (i == signal_after) signal(); }
     };
 
     // Every valid band filters and the launch is whole blocks: the chain runs continuously across the launch's blocks,
@@ -563,21 +568,25 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     issue_stage(0);
     if (continuous) {
         for (int t = 0; t < p.n_blocks; ++t) {
-            wait_stage(t);
+            // block t's rows have landed (TMA); every EQ warp is past block t-1 (the EMPTY barrier below doubles as the
+            // EQ warps' own barrier from the third block on), so block t+1's copies may overwrite the other buffer
+            mbar_wait(&stage_full[t & 1], (unsigned)((t >> 1) & 1));
+            fence_proxy_async();
             if (t >= 2) bar_sync(kBarEmpty0 + (t & 1), kCount);  // ring slot t%3 was last read as history of block t-2
+            else if (SM::kEqWarps > 1) bar_sync(kBarEq, SM::kEqThreads);
+            else __syncwarp();
+            if (t + 1 < p.n_blocks) issue_stage(t + 1);
             const float* row = stage + ((size_t)(t & 1) * G + g) * SM::kStageStride + ch * B;
             float* dcur = ring_c + (t % 3) * 2 * B;
             float* dprev_end = ring_c + ((t + 2) % 3) * 2 * B + B;  // one past the previous block's row
-            // first kLagA steps: the first band starts block t while the last band finishes block t-1
+            // during the first kLagA steps the first band starts block t while the last band finishes block t-1
             if (t == 0) {
 #pragma unroll 1
                 for (int i = 0; i < kLagA; i += DL) checked_iter(ld_in(row, i), i - DL * l, B, dcur);
+                fast_run(row, kLagA, B, dprev_end, dcur, -1, 0);
             } else {
-                fast_run(row, 0, kLagA, dprev_end, dcur);
-                __threadfence_block();
-                bar_arrive(kBarFull0 + ((t - 1) & 1), kCount);
+                fast_run(row, 0, B, dprev_end, dcur, kLagA - DL, kBarFull0 + ((t - 1) & 1));
             }
-            fast_run(row, kLagA, B, dprev_end, dcur);
         }
         {
             // drain: the first band has no more input; flush the three outputs the last fast iteration left pending,
