@@ -41,6 +41,8 @@ def is_stale() -> bool:
     not trusted: the snapshot that carries the prebuilt .so to the GPU box does not preserve them."""
     if not os.path.exists(LIB):
         return True
+    if os.environ.get("OHS_LIB_OVERRIDE"):
+        return False  # an explicitly chosen library (A/B experiments) is used as it is
     try:
         with open(LIB + ".srchash") as f:
             return f.read().strip() != _source_hash()

@@ -42,8 +42,9 @@ constexpr int kEqBandsPerLane = 2;
 constexpr int kEqGroup = kMaxBands / kEqBandsPerLane;  // lanes per (stream, channel) chain in an EQ warp
 constexpr int kEqChainsPerWarp = 32 / kEqGroup;
 constexpr int kMaxG = 7;       // streams per CTA; their 2G chains of 5 lanes are spread over ceil(G/3) EQ warps
-constexpr int kEqSkew = 8;     // steps between neighbouring lanes of the systolic chain: a shuffled value is consumed 7 steps
-                               // (~200 cycles) after it was sent, which rides out shared-memory-pipe contention from the FFT warps
+constexpr int kEqSkew = 4;     // steps between neighbouring lanes of the systolic chain: a shuffled value is consumed 3 steps
+                               // (~90 cycles) after it was sent.  8 was better while the FFT warps were heavier; on the final
+                               // kernel 4 wins (948 k vs 908 k stream-s/s: fewer live registers, shorter fill and drain)
 constexpr int kEqCoefStride = 8;  // floats per (eq_set, band): b0 b1 b2 a1 a2 enabled pad pad
 
 enum NamedBarrier { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarEq = 5, kBarConv = 6, kBarStream0 = 7 };
