@@ -41,6 +41,9 @@ constexpr int kMaxBands = 10;
 constexpr int kEqBandsPerLane = 2;
 constexpr int kEqGroup = kMaxBands / kEqBandsPerLane;  // lanes per (stream, channel) chain in an EQ warp
 constexpr int kEqChainsPerWarp = 32 / kEqGroup;
+#ifndef OHS_EQ_WEIGHT
+#define OHS_EQ_WEIGHT 4
+#endif
 constexpr int kMaxG = 7;       // streams per CTA; their 2G chains of 5 lanes are spread over ceil(G/3) EQ warps
 constexpr int kEqSkew = 4;     // steps between neighbouring lanes of the systolic chain: a shuffled value is consumed 3 steps
                                // (~90 cycles) after it was sent.  8 was better while the FFT warps were heavier; on the final
@@ -113,6 +116,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+    unsigned done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     unsigned done;
@@ -313,34 +322,42 @@ template <int N, int G> struct RenderSmem {
     static constexpr int kEqWarps = (2 * G + kEqChainsPerWarp - 1) / kEqChainsPerWarp;  // 3 (or 6) chains per EQ warp
     static constexpr int kEqThreads = 32 * kEqWarps;
     static constexpr int kConvWarps = G * T / 32;
-    static constexpr int kWorkers = kEqThreads + G * T;       // threads that take part in the named barriers
+    static constexpr int kWorkers = kEqThreads + G * T;       // threads that take part in the EMPTY barriers
+    static constexpr int kFullCount = kWorkers + 32;          // ... and in the FULL barriers: the staging warp listens in
     // Warp placement.  A warp's scheduler partition is (warp id mod 4) and an EQ warp carries three to four times the
     // instructions of a convolution warp, so the roles are spread to equalise the partitions' load: EQ warp w sits on
     // partition w (warp id w); each convolution warp goes to the least-loaded partition; unused warp slots exit at
     // once.  (Config 2, G = 7: partitions 0-2 hold one EQ + one convolution warp, partition 3 four convolution warps.)
     struct Placement {
         int conv_warp_id[kConvWarps > 0 ? kConvWarps : 1];
+        int stager_warp_id;   // the warp that issues the input rows' TMA copies (a few instructions per block)
         int total_warps;
     };
     // Balancing pads the CTA with idle warp slots, which only pays when one CTA owns the SM (N >= 512: config 2 and the
     // long-BRIR config); smaller transforms run several CTAs per SM, which balances the partitions by itself, and
     // there the roles are packed densely.
     static constexpr bool kBalanced = (N >= 512);
+    static constexpr int kEqWeight = OHS_EQ_WEIGHT;   // an EQ warp's load in units of a convolution warp's
     static constexpr Placement place() {
         Placement pl{};
         if (!kBalanced) {
             for (int f = 0; f < kConvWarps; ++f) pl.conv_warp_id[f] = kEqWarps + f;
-            pl.total_warps = kEqWarps + kConvWarps;
+            pl.stager_warp_id = kEqWarps + kConvWarps;
+            pl.total_warps = kEqWarps + kConvWarps + 1;
             return pl;
         }
         int load[4] = {0, 0, 0, 0}, count[4] = {0, 0, 0, 0};
-        for (int w = 0; w < kEqWarps; ++w) { load[w & 3] += 4; count[w & 3] += 1; }
+        for (int w = 0; w < kEqWarps; ++w) { load[w & 3] += kEqWeight; count[w & 3] += 1; }
         for (int f = 0; f < kConvWarps; ++f) {
             int best = 3;
             for (int q = 3; q >= 0; --q) if (load[q] < load[best]) best = q;
             pl.conv_warp_id[f] = 4 * count[best] + best;
             load[best] += 1; count[best] += 1;
         }
+        int few = 0;
+        for (int q = 1; q < 4; ++q) if (count[q] < count[few]) few = q;
+        pl.stager_warp_id = 4 * count[few] + few;
+        count[few] += 1;
         int mx = 0;
         for (int q = 0; q < 4; ++q) if (count[q] > mx) mx = count[q];
         pl.total_warps = 4 * mx;
@@ -348,18 +365,23 @@ template <int N, int G> struct RenderSmem {
     }
     static constexpr int kThreads = 32 * place().total_warps;
     template <int F> static constexpr int kConvWarpId = place().conv_warp_id[F];
+    static constexpr int kStagerWarpId = place().stager_warp_id;
     static constexpr size_t kTwOff = 0;                                      // float2 tw[N]
     static constexpr size_t kZOff = kTwOff + sizeof(float2) * N;             // float2 z[G][2][NP]
     // per-stream strides carry a 16-byte pad so that neighbouring streams sit on different banks
     static constexpr int kRingStride = 6 * B + 4;    // float per stream: planar ring[G][3 slots][2 channels][B]
-    static constexpr int kStageStride = 2 * B + 4;   // float per stream and stage buffer: stage[2][G][2][B]
+    // stage[3 buffers][G][left row | pad | right row | pad]: the 16-byte pads put the six rows an EQ warp reads (three
+    // streams x two channels) on different banks
+    static constexpr int kStageBufs = 3;
+    static constexpr int kRowR = B + 4;              // offset of the right row behind the left row
+    static constexpr int kStageStride = 2 * B + 8;   // float per stream and stage buffer
     static constexpr size_t kRingOff = kZOff + sizeof(float2) * G * 2 * NP;
     static constexpr size_t kStageOff = kRingOff + sizeof(float) * G * kRingStride;
     // filter spectra of a shared single-set, few-partition HRIR (configs 1-3) are staged here once per launch
     static constexpr size_t kFiltSmemBytes = (N <= 512) ? 16 * 1024 : 0;
-    static constexpr size_t kFiltOff = kStageOff + sizeof(float) * 2 * G * kStageStride;
-    static constexpr size_t kMbarOff = kFiltOff + kFiltSmemBytes;  // uint64_t stage_full[2], filt_full[2]
-    static constexpr size_t kBytes = kMbarOff + 32;
+    static constexpr size_t kFiltOff = kStageOff + sizeof(float) * kStageBufs * G * kStageStride;
+    static constexpr size_t kMbarOff = kFiltOff + kFiltSmemBytes;  // uint64_t stage_full[3], filt_full[2]
+    static constexpr size_t kBytes = kMbarOff + 48;
     static constexpr bool kFits = kBytes <= 227 * 1024 && kThreads <= 1024;
     // Register budget.  Warps are allocated in groups of four; as many CTAs per SM as shared memory allows (up to
     // four) while every thread keeps at least 80 registers.
@@ -397,6 +419,7 @@ __device__ __forceinline__ float df2t_step(float x, float& s1, float& s2, float 
 // exists and consumed three steps later, so its 26-cycle latency never stalls the in-order warp, and the two bands of a
 // lane are two independent dependent-chains that cover each other's 4-cycle FP32 latency.  Every band's recurrence
 // is the strictly sequential reference recurrence (see df2t_step): bit-exact.
+template <bool V> struct Flag { static constexpr bool value = V; };
 template <int N, int G>
 __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned char* smem, int stream0, int w) {
     using SM = RenderSmem<N, G>;
@@ -442,69 +465,60 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
         bs1 = st[ch]; bs2 = st[2 + ch];
     }
 
-    // Stage loader: rows (g', c') of block t -> stage[t&1][g'][c'][0..B).  Whole blocks go by TMA: one thread arms the
-    // stage's mbarrier with the byte count and issues one bulk copy per row (B*4 contiguous bytes each); the EQ warps'
-    // critical path carries no copy instructions.  A ragged last block (EQ-only mode) uses plain guarded loads.
+    // Input rows: block t sits in stage buffer t % 3 once that buffer's mbarrier has completed its (t/3)-th phase.
+    // The copies are TMA bulk copies issued by a convolution warp (issue_input_stage below), three blocks ahead, so the
+    // EQ warps' critical path carries neither copy instructions nor a barrier for the buffer hand-over.  Only a ragged
+    // last block (EQ-only mode) is loaded here, with plain guarded loads.
     uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
-    auto issue_stage = [&](int t) {
-        float* dst_base = stage + (size_t)(t & 1) * G * SM::kStageStride;
-        const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
-        if (nb == B) {
-            // lane r of EQ warp 0 copies row r (2G <= 14 rows); lane 0 also arms the barrier.  A copy that completes before
-            // the arming only drives the transaction count negative; the phase still needs lane 0's arrival.
-            const int n_str = (p.n_streams - stream0) < G ? (p.n_streams - stream0) : G;
-            if (threadIdx.x == 0) mbar_expect_tx(&stage_full[t & 1], (unsigned)(n_str * 2 * B * sizeof(float)));
-            const int row = threadIdx.x;
-            if (row < 2 * n_str) {
-                const float* src = p.in + ((size_t)(stream0 + (row >> 1)) * 2 + (row & 1)) * p.row_stride + (size_t)t * B;
-                tma_load_1d(dst_base + (row >> 1) * SM::kStageStride + (row & 1) * B, src, (unsigned)(B * sizeof(float)), &stage_full[t & 1]);
-            }
-        } else {
-            for (int q = threadIdx.x; q < G * 2 * B; q += SM::kEqThreads) {
-                const int row = q / B, n = q - row * B;
-                const int sg = stream0 + (row >> 1);
-                if (sg < p.n_streams && n < nb)
-                    dst_base[(row >> 1) * SM::kStageStride + (row & 1) * B + n] =
-                        p.in[((size_t)sg * 2 + (row & 1)) * p.row_stride + (size_t)t * B + n];
-            }
-        }
-    };
-    // Block t's rows have landed when the stage's mbarrier completes its (t/2)-th phase.  The EQ warps then meet at
-    // their barrier, which proves that every EQ warp is done reading the other stage buffer (block t-1), so the copies
-    // of block t+1 may start overwriting it (generic-proxy reads ordered before the async-proxy writes by the fence).
     auto wait_stage = [&](int t) {
         const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
-        if (nb == B) mbar_wait(&stage_full[t & 1], (unsigned)((t >> 1) & 1));
-        fence_proxy_async();
+        if (nb == B) { mbar_wait(&stage_full[t % 3], (unsigned)((t / 3) & 1)); return; }
+        float* dst_base = stage + (size_t)(t % 3) * G * SM::kStageStride;  // last read three blocks ago
+        for (int q = threadIdx.x; q < G * 2 * B; q += SM::kEqThreads) {
+            const int row = q / B, n = q - row * B;
+            const int sg = stream0 + (row >> 1);
+            if (sg < p.n_streams && n < nb)
+                dst_base[(row >> 1) * SM::kStageStride + (row & 1) * SM::kRowR + n] =
+                    p.in[((size_t)sg * 2 + (row & 1)) * p.row_stride + (size_t)t * B + n];
+        }
         if (SM::kEqWarps > 1) bar_sync(kBarEq, SM::kEqThreads); else __syncwarp();
-        if (t + 1 < p.n_blocks) issue_stage(t + 1);
     };
 
     const int src_lane = (l == 0) ? lane : lane - 1;
     const bool first = (l == 0), last = (l == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
-    float xs[DL], yl[DL];  // xs: band-A inputs of the next DL steps, shuffled over from lane l-1;  yl: last DL band-B outputs
+    // xsel[u]: band A's input at step u of the coming iteration, already chosen between the staged input sample (first
+    // lane of a chain) and lane l-1's shuffled output.  The choice is made right behind the shuffle, an iteration ahead
+    // of its use: ptxas gives a value whose only consumer lies behind the loop's back-edge the lowest priority and
+    // sinks its shuffle to the end of the loop body, a few instructions ahead of the consumer (~20 stall cycles per
+    // iteration in the SASS of the previous form).  yl: the last DL band-B outputs.
+    float xsel[DL], yl[DL];
 #pragma unroll
-    for (int u = 0; u < DL; ++u) { xs[u] = 0.f; yl[u] = 0.f; }
+    for (int u = 0; u < DL; ++u) { xsel[u] = 0.f; yl[u] = 0.f; }
     float ya_prev = 0.f;   // this lane's band-A output of the previous step
     struct In { float4 q[NQ]; };
     auto in_at = [&](const In& in, int u) { const float4 v = in.q[u >> 2]; return (u & 3) == 0 ? v.x : (u & 3) == 1 ? v.y : (u & 3) == 2 ? v.z : v.w; };
+    using SelNext = Flag<true>;
+    using SelLater = Flag<false>;
 
     // DL steady-state steps (local steps i0 .. i0+DL-1): every lane holds live samples (lanes of absent streams run on
-    // garbage that is never stored).  Whenever the last lane has completed an aligned group of four output samples
-    // ([i-kGrp, i-kGrp+3] at local step i, i % 4 == 0) it stores the group with one 16-byte store — into the previous
-    // block's ring slot while the group index is negative, into the current block's afterwards.
-    auto fast_iter = [&](const In& in, int i0, float* dprev_end, float* dcur) {
+    // garbage that is never stored).  `in`: this iteration's input samples, `nx`: the next iteration's.  Whenever the
+    // last lane has completed an aligned group of four output samples it stores the group with one 16-byte store at
+    // dst + (first sample's index relative to the block): the caller passes the end of the previous block's ring row
+    // during the first kLagA steps of a block (negative indices) and the block's own row afterwards.
+    // SelLater: the block's last iteration; the next block's rows may not have landed, the raw shuffled values stay in
+    // xsel and seed_inputs() completes them after the stage wait.
+    auto fast_iter = [&](auto sel, const In& in, const In& nx, int i0, float* dst) {
 #pragma unroll
         for (int u = 0; u < DL; ++u) {
-            const float xa = first ? in_at(in, u) : xs[u];  // shuffled over DL-1 steps ago
+            const float xa = xsel[u];
             const float y = df2t_step(ya_prev, bs1, bs2, bb0, bb1, bb2, ba1, ba2);   // band B on band A's previous output
             ya_prev = df2t_step(xa, as1, as2, ab0, ab1, ab2, aa1, aa2);
-            xs[(u + DL - 1) % DL] = __shfl_sync(0xffffffffu, y, src_lane);
-            if ((u & 3) == kStoreU && last) {
-                const int g0 = i0 + u - 3 - kOutLag;
-                float* dstp = (g0 < 0 ? dprev_end : dcur) + g0;
-                *reinterpret_cast<float4*>(dstp) = make_float4(yl[(u + DL - 3) % DL], yl[(u + DL - 2) % DL], yl[(u + DL - 1) % DL], y);
-            }
+            const float r = __shfl_sync(0xffffffffu, y, src_lane);   // band A's input DL-1 steps from now
+            if (u == 0) xsel[DL - 1] = first ? in_at(in, DL - 1) : r;
+            else xsel[u - 1] = (decltype(sel)::value && first) ? in_at(nx, u - 1) : r;
+            if ((u & 3) == kStoreU && last)
+                *reinterpret_cast<float4*>(dst + (i0 + u - 3 - kOutLag)) =
+                    make_float4(yl[(u + DL - 3) % DL], yl[(u + DL - 2) % DL], yl[(u + DL - 1) % DL], y);
             yl[u] = y;
         }
     };
@@ -512,12 +526,12 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     // where a band holds a live sample; a disabled band passes its input through and keeps its state
     // (src/dsp/parametric_eq.rs:118-120).  na0 = band A's sample index at the first of the steps; live samples
     // are [0, nb); the last lane stores sample by sample into dst0[n].
-    auto checked_iter = [&](const In& in, int na0, int nb, float* dst0) {
+    auto checked_iter = [&](const In& in, const In& nx, int na0, int nb, float* dst0) {
 #pragma unroll
         for (int u = 0; u < DL; ++u) {
             const int na = na0 + u, nbi = na - 1;
             const bool act_a = lane_valid && na >= 0 && na < nb, act_b = lane_valid && nbi >= 0 && nbi < nb;
-            const float xa = first ? in_at(in, u) : xs[u];
+            const float xa = xsel[u];
             float t1 = bs1, t2 = bs2;
             float y = df2t_step(ya_prev, t1, t2, bb0, bb1, bb2, ba1, ba2);
             const bool upd_b = act_b && en_b;
@@ -528,12 +542,14 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             const bool upd_a = act_a && en_a;
             as1 = upd_a ? t1 : as1; as2 = upd_a ? t2 : as2;
             ya_prev = upd_a ? ya : xa;
-            xs[(u + DL - 1) % DL] = __shfl_sync(0xffffffffu, y, src_lane);
+            const float r = __shfl_sync(0xffffffffu, y, src_lane);
+            if (u == 0) xsel[DL - 1] = first ? in_at(in, DL - 1) : r;
+            else xsel[u - 1] = first ? in_at(nx, u - 1) : r;
             if (act_b && last) dst0[nbi] = y;
             yl[u] = y;
         }
     };
-    // input samples [i, i+DL) of a staged row (zeros past the end of the block)
+    // input samples [i, i+DL) of a staged row: zeros past the end of the block ...
     auto ld_in = [&](const float* row, int i) {
         In in;
 #pragma unroll
@@ -541,24 +557,19 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             in.q[q] = (i + 4 * q < B) ? *reinterpret_cast<const float4*>(row + i + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
         return in;
     };
-    // steady-state iterations covering local steps [i0, i1); inputs are loaded one iteration ahead
-    // `signal_after` (a multiple of DL, or -1): once the iteration starting there is done the previous block is complete in
-    // the ring and the convolution warps are released.
-    auto fast_run = [&](const float* row, int i0, int i1, float* dprev_end, float* dcur, int signal_after, int full_id) {
-        auto signal = [&]() { __threadfence_block(); bar_arrive(full_id, kCount); };
-        In a = ld_in(row, i0), b;
-        int i = i0;
-#pragma unroll 1
-        for (; i + 2 * DL <= i1; i += 2 * DL) {
-            b = ld_in(row, i + DL);
-            fast_iter(a, i, dprev_end, dcur);
-            if (i == signal_after) signal();
-            a = ld_in(row, i + 2 * DL);
-            fast_iter(b, i + DL, dprev_end, dcur);
-            if (i + DL == signal_after) signal();
-        }
-        if (i < i1) { fast_iter(a, i, dprev_end, dcur); if (i == signal_after) signal(); }
+    // ... or, for the steady state's look-ahead loads, whatever follows: i <= B stays inside the stream's stage rows
+    // (the right row, or the 4-float pad behind it), and what is read there is never used
+    // Only a chain's first lane uses the samples: the load is predicated on it (6 active lanes, conflict-free rows).
+    static_assert(NQ == 1 && SM::kRowR >= B + 4 && SM::kStageStride >= SM::kRowR + B + 4, "look-ahead load of the last iteration reads the pad");
+    auto ld_fast = [&](In& in, const float* row, int i) { if (first) in.q[0] = *reinterpret_cast<const float4*>(row + i); };
+    // a block's first DL-1 inputs: taken from the staged row by the first lane, already in flight (shuffled) elsewhere
+    auto seed_inputs = [&](const In& in0, bool keep) {
+#pragma unroll
+        for (int u = 0; u < DL - 1; ++u) xsel[u] = first ? in_at(in0, u) : (keep ? xsel[u] : 0.f);
     };
+    // the stores of the first kLagA steps all belong to the previous block, all later ones to the block itself
+    static_assert(kLagA - DL + kStoreU + (DL - 1 - kStoreU) / 4 * 4 - 3 - kOutLag < 0 && kLagA + kStoreU - 3 - kOutLag >= 0 &&
+                  (B - kLagA) % (2 * DL) == DL, "block = head iterations + pairs of iterations + one last iteration");
 
     // Every valid band filters and the launch is whole blocks: the chain runs continuously across the launch's blocks,
     // filling once at the start and draining once at the end.
@@ -566,28 +577,43 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     const bool all_fast = __all_sync(0xffffffffu, lane_fast);
     const bool continuous = do_eq && p.tail_frames == B && (SM::kEqWarps > 1 ? __syncthreads_and_eq<SM::kEqThreads>(all_fast) : all_fast);
     float* ring_c = ring_f + (size_t)g * SM::kRingStride + ch * B;  // this chain's channel row of slot 0 (slots are 2*B apart)
-    issue_stage(0);
     if (continuous) {
+        bool landed = false;  // block t's rows were already seen complete (polled during the previous block)
+        int sb = 0; unsigned sphase = 0;  // stage buffer t % 3 and its phase (t / 3) & 1
         for (int t = 0; t < p.n_blocks; ++t) {
-            // block t's rows have landed (TMA); every EQ warp is past block t-1 (the EMPTY barrier below doubles as the
-            // EQ warps' own barrier from the third block on), so block t+1's copies may overwrite the other buffer
-            mbar_wait(&stage_full[t & 1], (unsigned)((t >> 1) & 1));
-            fence_proxy_async();
+            if (!landed) mbar_wait(&stage_full[sb], sphase);
             if (t >= 2) bar_sync(kBarEmpty0 + (t & 1), kCount);  // ring slot t%3 was last read as history of block t-2
-            else if (SM::kEqWarps > 1) bar_sync(kBarEq, SM::kEqThreads);
-            else __syncwarp();
-            if (t + 1 < p.n_blocks) issue_stage(t + 1);
-            const float* row = stage + ((size_t)(t & 1) * G + g) * SM::kStageStride + ch * B;
+            const float* row = stage + ((size_t)sb * G + g) * SM::kStageStride + ch * SM::kRowR;
             float* dcur = ring_c + (t % 3) * 2 * B;
-            float* dprev_end = ring_c + ((t + 2) % 3) * 2 * B + B;  // one past the previous block's row
+            In a = ld_in(row, 0), b = a;
+            seed_inputs(a, true);
             // during the first kLagA steps the first band starts block t while the last band finishes block t-1
             if (t == 0) {
 #pragma unroll 1
-                for (int i = 0; i < kLagA; i += DL) checked_iter(ld_in(row, i), i - DL * l, B, dcur);
-                fast_run(row, kLagA, B, dprev_end, dcur, -1, 0);
+                for (int i = 0; i < kLagA; i += DL) { b = ld_in(row, i + DL); checked_iter(a, b, i - DL * l, B, dcur); a = b; }
             } else {
-                fast_run(row, 0, B, dprev_end, dcur, kLagA - DL, kBarFull0 + ((t - 1) & 1));
+                float* dprev_end = ring_c + ((t + 2) % 3) * 2 * B + B;  // one past the previous block's row
+#pragma unroll 1
+                for (int i = 0; i < kLagA; i += DL) { ld_fast(b, row, i + DL); fast_iter(SelNext{}, a, b, i, dprev_end); a = b; }
+                // the previous block is complete in the ring: release the convolution warps (the barrier orders the
+                // shared-memory stores before the arrival for the threads that synchronise on it)
+                bar_arrive(kBarFull0 + ((t - 1) & 1), SM::kFullCount);
             }
+            // poll the next block's rows (issued two blocks ago) here, a block ahead of their use: the ~90-cycle
+            // mbarrier round trip stays off the block boundary
+            if (++sb == 3) { sb = 0; sphase ^= 1u; }
+            landed = (t + 1 < p.n_blocks) && mbar_try_wait(&stage_full[sb], sphase);
+            // the rest of the block: pairs of iterations with the inputs loaded one iteration ahead, then the last one
+            ld_fast(b, row, kLagA + DL);
+            int i = kLagA;
+#pragma unroll 1
+            for (; i + 2 * DL < B; i += 2 * DL) {
+                fast_iter(SelNext{}, a, b, i, dcur);
+                ld_fast(a, row, i + 2 * DL);
+                fast_iter(SelNext{}, b, a, i + DL, dcur);
+                ld_fast(b, row, i + 3 * DL);
+            }
+            fast_iter(SelLater{}, a, a, i, dcur);
         }
         {
             // drain: the first band has no more input; flush the three outputs the last fast iteration left pending,
@@ -600,10 +626,10 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             In zero;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) zero.q[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            seed_inputs(zero, true);
 #pragma unroll 1
-            for (int i = 0; i < kOutLag; i += DL) checked_iter(zero, B + i - DL * l, B, dl);
-            __threadfence_block();
-            bar_arrive(kBarFull0 + ((p.n_blocks - 1) & 1), kCount);
+            for (int i = 0; i < kOutLag; i += DL) checked_iter(zero, zero, B + i - DL * l, B, dl);
+            bar_arrive(kBarFull0 + ((p.n_blocks - 1) & 1), SM::kFullCount);
         }
     } else {
         for (int t = 0; t < p.n_blocks; ++t) {
@@ -611,29 +637,61 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             if (t >= 2) bar_sync(kBarEmpty0 + (t & 1), kCount);
             const int slot = t % 3;
             const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
-            const float* st_base = stage + (size_t)(t & 1) * G * SM::kStageStride;
+            const float* st_base = stage + (size_t)(t % 3) * G * SM::kStageStride;
             if (!do_eq) {
                 // EQ off (src/lib.rs:1179): the EQ warps only move the rows into the ring
                 for (int q = threadIdx.x; q < G * 2 * B; q += SM::kEqThreads) {
                     const int gg = q / (2 * B), n = q - gg * 2 * B;  // n runs over [left row | right row]
-                    ring_f[gg * SM::kRingStride + slot * 2 * B + n] = st_base[gg * SM::kStageStride + n];
+                    ring_f[gg * SM::kRingStride + slot * 2 * B + n] = st_base[gg * SM::kStageStride + (n < B ? n : n - B + SM::kRowR)];
                 }
             } else {
                 // per-block chain (ragged last block and/or disabled bands): fill, run and drain inside the block
-                const float* row = st_base + g * SM::kStageStride + ch * B;
+                const float* row = st_base + g * SM::kStageStride + ch * SM::kRowR;
                 float* dst = ring_c + slot * 2 * B;
-#pragma unroll
-                for (int u = 0; u < DL; ++u) xs[u] = 0.f;
+                In a = ld_in(row, 0), b;
+                seed_inputs(a, false);
+                xsel[DL - 1] = 0.f;
                 ya_prev = 0.f;
 #pragma unroll 1
-                for (int i = 0; i < nb + kOutLag; i += DL) checked_iter(ld_in(row, i), i - DL * l, nb, dst);
+                for (int i = 0; i < nb + kOutLag; i += DL) { b = ld_in(row, i + DL); checked_iter(a, b, i - DL * l, nb, dst); a = b; }
             }
-            __threadfence_block();
-            bar_arrive(kBarFull0 + (t & 1), kCount);
+            bar_arrive(kBarFull0 + (t & 1), SM::kFullCount);
         }
     }
     if (has_a) { float* st = reinterpret_cast<float*>(p.eqs + (size_t)s * kMaxBands + band_a); st[ch] = as1; st[2 + ch] = as2; }
     if (has_b) { float* st = reinterpret_cast<float*>(p.eqs + (size_t)s * kMaxBands + band_b); st[ch] = bs1; st[2 + ch] = bs2; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// staging warp
+// ---------------------------------------------------------------------------------------------------------------
+// Issues the TMA bulk copies of the input rows (HBM -> stage buffer t % 3; one copy of B*4 contiguous bytes per row by
+// lane = row, lane 0 arms the buffer's mbarrier with the byte count), three blocks ahead.  Buffer t % 3 is free once
+// every EQ thread has arrived at block t-3's FULL barrier (it read the rows before it arrived); the warp listens in on
+// that barrier and otherwise sleeps, so neither the EQ warps nor the convolution warps carry copy instructions.  A
+// ragged last block is loaded by the EQ warps themselves (eq_warp_main::wait_stage).
+template <int N, int G>
+__device__ __forceinline__ void stager_warp_main(const RenderParams& p, unsigned char* smem, int stream0) {
+    using SM = RenderSmem<N, G>;
+    constexpr int B = SM::B;
+    const int n_str = (p.n_streams - stream0) < G ? (p.n_streams - stream0) : G;
+    const int row = threadIdx.x & 31;   // 2G <= 14 rows
+    auto issue = [&](int t) {
+        if (t >= p.n_blocks || (t == p.n_blocks - 1 && p.tail_frames != B)) return;
+        uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff) + (t % 3);
+        float* dst_base = reinterpret_cast<float*>(smem + SM::kStageOff) + (size_t)(t % 3) * G * SM::kStageStride;
+        fence_proxy_async();            // the async-proxy writes stay behind the generic-proxy reads ordered by the barrier
+        if (row == 0) mbar_expect_tx(full, (unsigned)(n_str * 2 * B * sizeof(float)));
+        if (row < 2 * n_str) {
+            const float* src = p.in + ((size_t)(stream0 + (row >> 1)) * 2 + (row & 1)) * p.row_stride + (size_t)t * B;
+            tma_load_1d(dst_base + (row >> 1) * SM::kStageStride + (row & 1) * SM::kRowR, src, (unsigned)(B * sizeof(float)), full);
+        }
+    };
+    issue(0); issue(1); issue(2);
+    for (int t = 0; t < p.n_blocks; ++t) {   // every block: the barriers count this warp
+        bar_sync(kBarFull0 + (t & 1), SM::kFullCount);
+        issue(t + 3);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -713,7 +771,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     constexpr int kPairs = N / 4 / T;
     // TMA filter-tile pipeline (see the block loop): needs two streams' FFT buffers as tile buffers, one shared set with
     // more partitions than fit the resident table, and every conv thread of the CTA taking part
-    uint64_t* filt_full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff) + 2;
+    uint64_t* filt_full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff) + 3;
     unsigned filt_phase[2] = {0u, 0u};
     constexpr bool kTmaFilterPath = (G >= 2) && (N >= 1024);  // compiled only where long responses live (register budget)
     if (kTmaFilterPath && p.uniform_set && !valid) nparts = p.set_parts[0];  // threads of an absent stream still run the tile loop
@@ -843,7 +901,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
                     if (mm == m) { acc[mm][0] = a4[0]; acc[mm][1] = a4[1]; acc[mm][2] = a4[2]; acc[mm][3] = a4[3]; }
             }
         }
-        bar_sync(kBarFull0 + (t & 1), kCount);
+        bar_sync(kBarFull0 + (t & 1), SM::kFullCount);
         const int cur = t % 3, prv = (t + 2) % 3;
         const float* xc = ring_g + cur * 2 * B;
         const float* xp = ring_g + prv * 2 * B;
@@ -934,8 +992,9 @@ __global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const Re
             uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
             mbar_init(&stage_full[0], 1);
             mbar_init(&stage_full[1], 1);
-            mbar_init(&stage_full[2], 1);  // filt_full[0..1]: filter tiles of the long-impulse-response path
-            mbar_init(&stage_full[3], 1);
+            mbar_init(&stage_full[2], 1);
+            mbar_init(&stage_full[3], 1);  // filt_full[0..1]: filter tiles of the long-impulse-response path
+            mbar_init(&stage_full[4], 1);
             fence_mbar_init();
         }
         if (p.filt_in_smem) {
@@ -948,6 +1007,7 @@ __global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const Re
     __syncthreads();
     const int warp = threadIdx.x >> 5;
     if (warp < SM::kEqWarps) { eq_warp_main<N, G>(p, smem, stream0, warp); return; }
+    if (warp == SM::kStagerWarpId) { stager_warp_main<N, G>(p, smem, stream0); return; }
     const int conv_index = find_conv_index<N, G>(warp, std::make_integer_sequence<int, SM::kConvWarps>{});
     if (conv_index >= 0) conv_warps_main<N, G>(p, smem, stream0, conv_index);  // other warp slots are placement padding
 }
