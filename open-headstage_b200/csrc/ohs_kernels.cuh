@@ -369,7 +369,11 @@ template <int N, int G> struct RenderSmem {
     static constexpr size_t kTwOff = 0;                                      // float2 tw[N]
     static constexpr size_t kZOff = kTwOff + sizeof(float2) * N;             // float2 z[G][2][NP]
     // per-stream strides carry a 16-byte pad so that neighbouring streams sit on different banks
-    static constexpr int kRingStride = 6 * B + 4;    // float per stream: planar ring[G][3 slots][2 channels][B]
+    // planar ring[G][3 slots][left row | pad | right row | pad]: streams 16 bytes apart in bank space, a stream's two
+    // rows 64 bytes apart, so the six rows an EQ warp stores to in one instruction sit on different banks
+    static constexpr int kRingRowR = B + 16;                 // offset of the right row behind the left row
+    static constexpr int kRingSlot = 2 * B + 32;             // floats per slot (a multiple of 32: slots share banks)
+    static constexpr int kRingStride = 3 * kRingSlot + 4;    // floats per stream
     // stage[3 buffers][G][left row | pad | right row | pad]: the 16-byte pads put the six rows an EQ warp reads (three
     // streams x two channels) on different banks
     static constexpr int kStageBufs = 3;
@@ -437,8 +441,10 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     float* stage = reinterpret_cast<float*>(smem + SM::kStageOff);
 
     const int lane = threadIdx.x & 31;
-    const int c_raw = kEqChainsPerWarp * w + lane / kEqGroup;  // chain index in the CTA: 2*stream + channel
-    const int l = lane % kEqGroup;
+    // band-major lanes: lane = l * 6 + chain.  The six first lanes (input loads) and the six last lanes (output stores)
+    // each fall into one quarter-warp, so a 128-bit shared-memory access of theirs is a single wavefront.
+    const int c_raw = kEqChainsPerWarp * w + lane % kEqChainsPerWarp;  // chain index in the CTA: 2*stream + channel
+    const int l = lane / kEqChainsPerWarp;
     const bool chain_ok = (lane < kEqChainsPerWarp * kEqGroup) && (c_raw < 2 * G);
     const int c = chain_ok ? c_raw : 0;
     const int g = c >> 1, ch = c & 1;
@@ -484,7 +490,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
         if (SM::kEqWarps > 1) bar_sync(kBarEq, SM::kEqThreads); else __syncwarp();
     };
 
-    const int src_lane = (l == 0) ? lane : lane - 1;
+    const int src_lane = (l == 0) ? lane : lane - kEqChainsPerWarp;
     const bool first = (l == 0), last = (l == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
     // xsel[u]: band A's input at step u of the coming iteration, already chosen between the staged input sample (first
     // lane of a chain) and lane l-1's shuffled output.  The choice is made right behind the shuffle, an iteration ahead
@@ -576,7 +582,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     const bool lane_fast = !lane_valid || !do_eq || (en_a && has_a && en_b && has_b);
     const bool all_fast = __all_sync(0xffffffffu, lane_fast);
     const bool continuous = do_eq && p.tail_frames == B && (SM::kEqWarps > 1 ? __syncthreads_and_eq<SM::kEqThreads>(all_fast) : all_fast);
-    float* ring_c = ring_f + (size_t)g * SM::kRingStride + ch * B;  // this chain's channel row of slot 0 (slots are 2*B apart)
+    float* ring_c = ring_f + (size_t)g * SM::kRingStride + ch * SM::kRingRowR;  // this chain's channel row of slot 0
     if (continuous) {
         bool landed = false;  // block t's rows were already seen complete (polled during the previous block)
         int sb = 0; unsigned sphase = 0;  // stage buffer t % 3 and its phase (t / 3) & 1
@@ -584,7 +590,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             if (!landed) mbar_wait(&stage_full[sb], sphase);
             if (t >= 2) bar_sync(kBarEmpty0 + (t & 1), kCount);  // ring slot t%3 was last read as history of block t-2
             const float* row = stage + ((size_t)sb * G + g) * SM::kStageStride + ch * SM::kRowR;
-            float* dcur = ring_c + (t % 3) * 2 * B;
+            float* dcur = ring_c + (t % 3) * SM::kRingSlot;
             In a = ld_in(row, 0), b = a;
             seed_inputs(a, true);
             // during the first kLagA steps the first band starts block t while the last band finishes block t-1
@@ -592,7 +598,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
 #pragma unroll 1
                 for (int i = 0; i < kLagA; i += DL) { b = ld_in(row, i + DL); checked_iter(a, b, i - DL * l, B, dcur); a = b; }
             } else {
-                float* dprev_end = ring_c + ((t + 2) % 3) * 2 * B + B;  // one past the previous block's row
+                float* dprev_end = ring_c + ((t + 2) % 3) * SM::kRingSlot + B;  // one past the previous block's row
 #pragma unroll 1
                 for (int i = 0; i < kLagA; i += DL) { ld_fast(b, row, i + DL); fast_iter(SelNext{}, a, b, i, dprev_end); a = b; }
                 // the previous block is complete in the ring: release the convolution warps (the barrier orders the
@@ -618,7 +624,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
         {
             // drain: the first band has no more input; flush the three outputs the last fast iteration left pending,
             // then run the remaining steps checked (sample by sample stores)
-            float* dl = ring_c + ((p.n_blocks - 1) % 3) * 2 * B;
+            float* dl = ring_c + ((p.n_blocks - 1) % 3) * SM::kRingSlot;
             if (last) {
 #pragma unroll
                 for (int e = 0; e < kPending; ++e) dl[B - kOutLag - kPending + e] = yl[DL - kPending + e];
@@ -642,12 +648,13 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
                 // EQ off (src/lib.rs:1179): the EQ warps only move the rows into the ring
                 for (int q = threadIdx.x; q < G * 2 * B; q += SM::kEqThreads) {
                     const int gg = q / (2 * B), n = q - gg * 2 * B;  // n runs over [left row | right row]
-                    ring_f[gg * SM::kRingStride + slot * 2 * B + n] = st_base[gg * SM::kStageStride + (n < B ? n : n - B + SM::kRowR)];
+                    ring_f[gg * SM::kRingStride + slot * SM::kRingSlot + (n < B ? n : n - B + SM::kRingRowR)] =
+                        st_base[gg * SM::kStageStride + (n < B ? n : n - B + SM::kRowR)];
                 }
             } else {
                 // per-block chain (ragged last block and/or disabled bands): fill, run and drain inside the block
                 const float* row = st_base + g * SM::kStageStride + ch * SM::kRowR;
-                float* dst = ring_c + slot * 2 * B;
+                float* dst = ring_c + slot * SM::kRingSlot;
                 In a = ld_in(row, 0), b;
                 seed_inputs(a, false);
                 xsel[DL - 1] = 0.f;
@@ -708,13 +715,13 @@ __device__ __forceinline__ void mac_bin(float2& acc, float2 u, float2 pu, float4
 // first-pass loader of the forward transform: the overlap-save window [previous block | current block] read from the
 // planar ring, z = left + i*right
 struct RingWindow {
-    const float* xp; const float* xc; int B;
+    const float* xp; const float* xc; int B; int R;  // R: offset of a slot's right row
     __device__ __forceinline__ float2 ld(int i) const {
-        return i < B ? make_float2(xp[i], xp[B + i]) : make_float2(xc[i - B], xc[i]);
+        return i < B ? make_float2(xp[i], xp[R + i]) : make_float2(xc[i - B], xc[R + i - B]);
     }
     __device__ __forceinline__ void ld2(int i, float2& a, float2& b) const {  // i even: samples i and i+1
         const float* row = i < B ? xp + i : xc + (i - B);
-        const float2 l = *reinterpret_cast<const float2*>(row), r = *reinterpret_cast<const float2*>(row + B);
+        const float2 l = *reinterpret_cast<const float2*>(row), r = *reinterpret_cast<const float2*>(row + R);
         a = make_float2(l.x, r.x); b = make_float2(l.y, r.y);
     }
 };
@@ -903,8 +910,8 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
         }
         bar_sync(kBarFull0 + (t & 1), SM::kFullCount);
         const int cur = t % 3, prv = (t + 2) % 3;
-        const float* xc = ring_g + cur * 2 * B;
-        const float* xp = ring_g + prv * 2 * B;
+        const float* xc = ring_g + cur * SM::kRingSlot;
+        const float* xp = ring_g + prv * SM::kRingSlot;
         const bool release = (t + 2 < p.n_blocks);
         if (!valid) {
             if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount);
@@ -915,13 +922,13 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
             const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
             for (int n = tid; n < nb; n += T) {
                 out_l[(size_t)t * B + n] = xc[n] * gain;
-                out_r[(size_t)t * B + n] = xc[B + n] * gain;
+                out_r[(size_t)t * B + n] = xc[SM::kRingRowR + n] * gain;
             }
             if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount);
             continue;
         }
         // ---- forward FFT of the overlap-save window [previous block | current block], z = left + i*right
-        fft_run<N, T>(tid, tw, b0, b1, RingWindow{xp, xc, B}, zbuf, stream_sync,
+        fft_run<N, T>(tid, tw, b0, b1, RingWindow{xp, xc, B, SM::kRingRowR}, zbuf, stream_sync,
                       [&]() { if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount); });
         stream_sync();
         // ---- this block's spectrum: into the delay line, and its product with partition 0 on top of the history
@@ -958,8 +965,8 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     }
     // overlap-save history for the next launch: the last filtered block
     if (valid && p.conv_enable && p.n_blocks > 0) {
-        const float* xc = ring_g + ((p.n_blocks - 1) % 3) * 2 * B;
-        for (int n = tid; n < B; n += T) p.prev[(size_t)s * B + n] = make_float2(xc[n], xc[B + n]);
+        const float* xc = ring_g + ((p.n_blocks - 1) % 3) * SM::kRingSlot;
+        for (int n = tid; n < B; n += T) p.prev[(size_t)s * B + n] = make_float2(xc[n], xc[SM::kRingRowR + n]);
     }
 }
 
@@ -985,8 +992,8 @@ __global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const Re
             const int g = q / SM::B, n = q - g * SM::B;
             const int s = stream0 + g;
             const float2 v = (s < p.n_streams) ? p.prev[(size_t)s * SM::B + n] : make_float2(0.f, 0.f);
-            ring[g * SM::kRingStride + 2 * 2 * SM::B + n] = v.x;
-            ring[g * SM::kRingStride + 2 * 2 * SM::B + SM::B + n] = v.y;
+            ring[g * SM::kRingStride + 2 * SM::kRingSlot + n] = v.x;
+            ring[g * SM::kRingStride + 2 * SM::kRingSlot + SM::kRingRowR + n] = v.y;
         }
         if (threadIdx.x == 0) {
             uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
