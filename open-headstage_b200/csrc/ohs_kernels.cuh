@@ -62,7 +62,7 @@ struct RenderParams {
     const int* stream_hrir;     // [stream] -> hrir set
     const int* stream_eq;       // [stream] -> eq set
     const float* stream_gain;   // [stream]
-    const float4* filt;         // [set][pmax][N] {A.re, A.im, C.re, C.im}, 1/N folded in
+    const float4* filt;         // [set][pmax][even bins | odd bins] {A.re, A.im, C.re, C.im}, 1/N folded in
     const int* set_parts;       // [set] partitions in use
     float2* fdl;                // [stream][pmax][N] packed spectra ring (unused when every set has 1 partition)
     float2* prev;               // [stream][B] last filtered input block (overlap-save history)
@@ -761,13 +761,15 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     float* ring_g = ring + (size_t)g * SM::kRingStride;  // planar: slot k = [left row | right row] at k*2*B
 
     int nparts = 1;
-    const float4* filt = p.filt;
+    const float4* filt = p.filt;      // all partitions: resident shared-memory copy or global (generic pointer)
+    const float4* filt_g = p.filt;    // the set's table in global memory
     float gain = 1.f;
     float2* fdl_s = nullptr;
     if (valid) {
         const int set = p.stream_hrir[s];
         nparts = p.set_parts[set];
         filt = p.filt_in_smem ? reinterpret_cast<const float4*>(smem + SM::kFiltOff) : p.filt + (size_t)set * p.pmax * N;
+        filt_g = p.filt + (size_t)set * p.pmax * N;
         gain = p.stream_gain[s];
         fdl_s = p.fdl + (size_t)s * p.pmax * N;
     }
@@ -785,11 +787,15 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     const bool tma_filters = kTmaFilterPath && p.uniform_set && !p.filt_in_smem && p.conv_enable && nparts > 1;
     // one delay-line partition's worth of operands of a bin pair: Z[k], Z[k+1], Z[mirror k], Z[mirror k+1] and their filters
     struct Operands { float4 uu; float2 v0, v1; float4 f0, f1, g0, g1; };
+    // a partition's filter table is stored even bins first, odd bins behind them (setup_filters_kernel): a warp's loads
+    // of its bins k = 2*lane, of k+1 and of the mirror bins are each contiguous across the lanes
+    auto fe = [](int j) { return j >> 1; };             // position of even bin j
+    auto fo = [](int j) { return N / 2 + (j >> 1); };   // position of odd bin j
     auto load_ops = [&](const float2* zq, const float4* fq, int k, int m0, int m1) {
         Operands o;
         o.uu = *reinterpret_cast<const float4*>(zq + k);
         o.v0 = zq[m0]; o.v1 = zq[m1];
-        o.f0 = fq[k]; o.f1 = fq[k + 1]; o.g0 = fq[m0]; o.g1 = fq[m1];
+        o.f0 = fq[fe(k)]; o.f1 = fq[fo(k + 1)]; o.g0 = fq[fe(m0)]; o.g1 = fq[fo(m1)];
         return o;
     };
     auto mac_ops = [&](float2 (&acc)[4], const Operands& o, int k) {
@@ -863,7 +869,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
                                 const int m0 = k ? N - k : N / 2, m1 = N - k - 1;
                                 Operands o;
                                 o.uu = zr[j][m].uu; o.v0 = zr[j][m].v0; o.v1 = zr[j][m].v1;
-                                o.f0 = fq[k]; o.f1 = fq[k + 1]; o.g0 = fq[m0]; o.g1 = fq[m1];
+                                o.f0 = fq[fe(k)]; o.f1 = fq[fo(k + 1)]; o.g0 = fq[fe(m0)]; o.g1 = fq[fo(m1)];
                                 mac_ops(acc[m], o, k);
                             }
                             if (q + 2 < nparts) load_z(zr[j], q + 2);
@@ -942,22 +948,28 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
                 dstz[i >> 1] = make_float4(z0.x, z0.y, z1.x, z1.y);
             }
         }
+        // partition 0's spectra come from the resident shared-memory copy (plain LDS: the address space is known at
+        // compile time) or from global memory; one generic pointer for both would compile to generic loads
+        auto mac_partition0 = [&](const float4* fq) {
 #pragma unroll
-        for (int m = 0; m < kPairs; ++m) {
-            const int k = 2 * (tid + m * T);
-            const int m0 = k ? N - k : N / 2, m1 = N - k - 1;
-            Operands o;
-            float2 u0, u1;
-            zbuf.ld2(k, u0, u1);
-            o.uu = make_float4(u0.x, u0.y, u1.x, u1.y);
-            o.v0 = zbuf.ld(m0); o.v1 = zbuf.ld(m1);
-            o.f0 = filt[k]; o.f1 = filt[k + 1]; o.g0 = filt[m0]; o.g1 = filt[m1];
-            mac_ops(acc[m], o, k);
-            // swap(re, im): the inverse transform is run as swap(FFT(swap(W)))
-            wbuf.st2(k, make_float2(acc[m][0].y, acc[m][0].x), make_float2(acc[m][1].y, acc[m][1].x));
-            wbuf.st(m0, make_float2(acc[m][2].y, acc[m][2].x));
-            wbuf.st(m1, make_float2(acc[m][3].y, acc[m][3].x));
-        }
+            for (int m = 0; m < kPairs; ++m) {
+                const int k = 2 * (tid + m * T);
+                const int m0 = k ? N - k : N / 2, m1 = N - k - 1;
+                Operands o;
+                float2 u0, u1;
+                zbuf.ld2(k, u0, u1);
+                o.uu = make_float4(u0.x, u0.y, u1.x, u1.y);
+                o.v0 = zbuf.ld(m0); o.v1 = zbuf.ld(m1);
+                o.f0 = fq[fe(k)]; o.f1 = fq[fo(k + 1)]; o.g0 = fq[fe(m0)]; o.g1 = fq[fo(m1)];
+                mac_ops(acc[m], o, k);
+                // swap(re, im): the inverse transform is run as swap(FFT(swap(W)))
+                wbuf.st2(k, make_float2(acc[m][0].y, acc[m][0].x), make_float2(acc[m][1].y, acc[m][1].x));
+                wbuf.st(m0, make_float2(acc[m][2].y, acc[m][2].x));
+                wbuf.st(m1, make_float2(acc[m][3].y, acc[m][3].x));
+            }
+        };
+        if (SM::kFiltSmemBytes > 0 && p.filt_in_smem) mac_partition0(reinterpret_cast<const float4*>(smem + SM::kFiltOff));
+        else mac_partition0(filt_g);
         stream_sync();
         // ---- inverse FFT; keep the last B samples (overlap-save), ear sums are already inside W, apply gain
         fft_run<N, T>(tid, tw, zbuf.p, wbuf.p, wbuf, OutputStore{out_l + (size_t)t * B - B, out_r + (size_t)t * B - B, gain, B},
@@ -1068,7 +1080,8 @@ __global__ void __launch_bounds__(SetupSmem<N>::T) setup_filters_kernel(const fl
     float4* dst = filt + ((size_t)set * pmax + part) * N;
     for (int k = tid; k < N; k += T) {
         const float2 l = gl.ld(k), r = gr.ld(k);
-        dst[k] = make_float4((l.x + r.y) * sc, (l.y - r.x) * sc, (l.x - r.y) * sc, (l.y + r.x) * sc);
+        // even bins first, odd bins behind them: the layout the convolution warps' lane-contiguous loads want
+        dst[(k & 1) * (N / 2) + (k >> 1)] = make_float4((l.x + r.y) * sc, (l.y - r.x) * sc, (l.x - r.y) * sc, (l.y + r.x) * sc);
     }
 }
 
