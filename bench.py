@@ -171,7 +171,9 @@ def run_reference(args, pkg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, cores, sample, ms = cpu_reference_run(pkg, args.steps, min(args.warmup, 1), seconds_per_stream=1.024)
+    # each step: 4 streams per host thread x 5.12 s of audio (~0.2 s of CPU work per step on 16 cores): long enough that
+    # thread start-up and cold caches do not understate the CPU path, short enough for any --steps the driver picks
+    value, cores, sample, ms = cpu_reference_run(pkg, args.steps, min(args.warmup, 1), seconds_per_stream=5.12)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
