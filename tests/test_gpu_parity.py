@@ -488,3 +488,45 @@ def test_repeated_runs_are_bit_identical():
         e.set_hrir_set(h); e.eq_set_preset(S.EQ_PRESET_TYPICAL); e.set_eq_enable(True); e.set_gain(0.5)
         outs.append(e.process(x).tobytes())
     assert len(set(outs)) == 1
+
+
+# ------------------------------------------------------------------------------------------------------------
+# launch lengths around the three-buffer input staging (1..7 blocks), every EQ path: the continuous systolic chain,
+# the per-block chain (a disabled band), EQ only with a ragged tail, EQ off
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_blocks", [1, 2, 3, 4, 5, 7])
+@pytest.mark.parametrize("mode", ["chain", "chain_disabled_band", "eq_only_ragged", "conv_only"])
+def test_short_launches_every_path(n_blocks, mode):
+    block, taps, n_streams = 256, 300, 9   # 9 streams: two CTAs at 7 streams per CTA would need >= 8; the last CTA is partial
+    n = block * n_blocks - (57 if mode == "eq_only_ragged" else 0)
+    x = S.stream_inputs(n_streams, n, base_seed=900 + n_blocks)
+    h = S.synthetic_hrir_set(taps, 50.0, seed=5)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL)
+    enabled = [1] * 10
+    e = ohs.Engine(n_streams, block, taps)
+    e.set_hrir_set(h)
+    if mode == "chain_disabled_band":
+        enabled[3] = 0
+    for b in range(10):
+        e.eq_set_band(b, coeffs[b], bool(enabled[b]))
+    if mode == "eq_only_ragged":
+        e.set_conv_enable(False); e.set_eq_enable(True)
+        y = e.process(x)
+        for s in range(n_streams):
+            q = O.StereoParametricEQ(10, FS)
+            for b in range(10):
+                q.set_band_raw(b, coeffs[b], True)
+            l, r = q.process_block(x[s, 0], x[s, 1])
+            assert y[s, 0].tobytes() == l.tobytes() and y[s, 1].tobytes() == r.tobytes()
+        return
+    if mode == "conv_only":
+        e.set_eq_enable(False)
+        ref = oracle_render(x, block, h)
+    else:
+        e.set_eq_enable(True)
+        ref = oracle_render(x, block, h, coeffs, enabled)
+    # two calls: the second starts from the first one's state
+    half = (n_blocks // 2) * block
+    y = np.concatenate([e.process(x[:, :, :half]), e.process(x[:, :, half:])], axis=2) if half else e.process(x)
+    err = float(np.max(np.abs(y - ref)))
+    assert err <= TOL, err
