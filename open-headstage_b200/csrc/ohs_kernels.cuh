@@ -322,6 +322,11 @@ template <int N, int G> struct RenderSmem {
     static constexpr int kEqWarps = (2 * G + kEqChainsPerWarp - 1) / kEqChainsPerWarp;  // 3 (or 6) chains per EQ warp
     static constexpr int kEqThreads = 32 * kEqWarps;
     static constexpr int kConvWarps = G * T / 32;
+    // Single-partition responses (config 2) at N = 512: the forward transform's last pass, the spectral product and the
+    // inverse transform's first pass run fused in registers (conv_warps_main).  Needs one warp per stream, equal first
+    // and last radices and two butterflies of the last pass per thread.
+    static constexpr bool kFusedMac = (T == 32) && (FftPlan<N, T>::kPasses == 3) && (FftPlan<N, T>::R1 == FftPlan<N, T>::R3) &&
+                                      (N / FftPlan<N, T>::R3 == 2 * T);
     static constexpr int kWorkers = kEqThreads + G * T;       // threads that take part in the EMPTY barriers
     static constexpr int kFullCount = kWorkers + 32;          // ... and in the FULL barriers: the staging warp listens in
     // Warp placement.  A warp's scheduler partition is (warp id mod 4) and an EQ warp carries three to four times the
@@ -933,6 +938,61 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
             if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount);
             continue;
         }
+        if constexpr (SM::kFusedMac) {
+            if (nparts == 1) {
+                // ---- single partition: forward passes 1 and 2 through shared memory; then the last forward pass, the
+                // spectral product and the first inverse pass in registers.  The last pass's butterfly i produces the
+                // bins i + q*NB (q < R), exactly the inputs of the inverse transform's first-pass butterfly i, and the
+                // mirror bins N - (i + q*NB) are the outputs NB-i + (R-1-q)*NB of butterfly NB-i: a thread that owns
+                // butterflies i and NB-i holds every operand of W[k] = Z[k] A[k] + conj(Z[N-k]) C[k] for its 2R bins.
+                // (Thread 0 owns the two self-mirrored butterflies 0 and NB/2.)  Same arithmetic in the same order as
+                // the general path, a third fewer shared-memory wavefronts and two fewer synchronisations per block.
+                constexpr int R = Pl::R3, NB = N / R;
+                const SmemCx c0{b0}, c1{b1};
+                fft_pass<N, T, Pl::R1, Pl::P1>(tid, tw, RingWindow{xp, xc, B, SM::kRingRowR}, c0);
+                if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount);
+                stream_sync();
+                fft_pass<N, T, Pl::R2, Pl::P2>(tid, tw + Pl::kTw2, c0, c1);
+                stream_sync();
+                const bool t0 = (tid == 0);
+                const int iu = tid, iv = t0 ? NB / 2 : NB - tid;
+                float2 u[R], v[R], wu[R], wv[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) { u[r] = c1.ld(iu + r * NB); v[r] = c1.ld(iv + r * NB); }
+                const float2* tw3 = tw + Pl::kTw3;   // w^{k r / N}, k < NB
+#pragma unroll
+                for (int r = 1; r < R; ++r) { u[r] = cmul(u[r], tw3[(r - 1) * NB + iu]); v[r] = cmul(v[r], tw3[(r - 1) * NB + iv]); }
+                Dft<R>::run(u);
+                Dft<R>::run(v);
+                auto product = [&](auto fld) {
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        const float2 mu = t0 ? u[(R - q) & (R - 1)] : v[R - 1 - q];
+                        const float2 mv = t0 ? v[R - 1 - q] : u[R - 1 - q];
+                        float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+                        mac_bin(a, u[q], mu, fld(iu + q * NB));
+                        mac_bin(b, v[q], mv, fld(iv + q * NB));
+                        wu[q] = make_float2(a.y, a.x);  // swap(re, im): the inverse transform is run as swap(FFT(swap(W)))
+                        wv[q] = make_float2(b.y, b.x);
+                    }
+                };
+                if (SM::kFiltSmemBytes > 0 && p.filt_in_smem) {
+                    const float4* fs = reinterpret_cast<const float4*>(smem + SM::kFiltOff);  // natural order (render_kernel)
+                    product([&](int k) { return fs[k]; });
+                } else {
+                    product([&](int k) { return filt_g[(k & 1) * (N / 2) + (k >> 1)]; });
+                }
+                Dft<R>::run(wu);
+                Dft<R>::run(wv);
+#pragma unroll
+                for (int q = 0; q < R; q += 2) { c0.st2(iu * R + q, wu[q], wu[q + 1]); c0.st2(iv * R + q, wv[q], wv[q + 1]); }
+                stream_sync();
+                fft_pass<N, T, Pl::R2, Pl::P2>(tid, tw + Pl::kTw2, c0, c1);
+                stream_sync();
+                fft_pass<N, T, Pl::R3, Pl::P3>(tid, tw + Pl::kTw3, c1, OutputStore{out_l + (size_t)t * B - B, out_r + (size_t)t * B - B, gain, B});
+                continue;
+            }
+        }
         // ---- forward FFT of the overlap-save window [previous block | current block], z = left + i*right
         fft_run<N, T>(tid, tw, b0, b1, RingWindow{xp, xc, B, SM::kRingRowR}, zbuf, stream_sync,
                       [&]() { if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount); });
@@ -1020,7 +1080,10 @@ __global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const Re
             // one shared HRIR set with few partitions: its spectra stay in shared memory for the whole launch
             float4* fs = reinterpret_cast<float4*>(smem + SM::kFiltOff);
             const int n4 = p.filt_in_smem * N;  // partitions * N
-            for (int i = threadIdx.x; i < n4; i += SM::kThreads) fs[i] = p.filt[i];
+            // the fused single-partition path reads bin k at position k; every other path keeps the global table's
+            // even-bins-first layout
+            const bool natural = SM::kFusedMac && p.filt_in_smem == 1;
+            for (int i = threadIdx.x; i < n4; i += SM::kThreads) fs[i] = natural ? p.filt[(i & 1) * (N / 2) + (i >> 1)] : p.filt[i];
         }
     }
     __syncthreads();
