@@ -7,13 +7,14 @@
 // src/dsp/convolution.rs:184-289, for many streams at once.
 //
 // Design (DESIGN.md §4 has the derivations, the measured pipe numbers and the ncu evidence behind each choice):
-//   * EQ warps: band-systolic in time.  Lane (c, l) owns bands 2l and 2l+1 of chain c = (stream, channel); at step s
-//     band A filters sample s-8l with the input shuffled over from lane l-1 seven steps earlier, band B filters sample
-//     s-8l-1 with band A's previous output.  Every band's recurrence stays strictly sequential in the reference's
+//   * staging warp: issues the TMA bulk copies of the input rows HBM -> shared memory (one per row, completing on an
+//     mbarrier) into a ring of three stage buffers, three blocks ahead.
+//   * EQ warps: band-systolic in time.  Lane l*6 + c owns bands 2l and 2l+1 of chain c = (stream, channel); at step s
+//     band A filters sample s-4l with the input shuffled over from lane l-1 three steps earlier, band B filters sample
+//     s-4l-1 with band A's previous output.  Every band's recurrence stays strictly sequential in the reference's
 //     operation order with explicitly rounded, never-contracted scalar ops: bit-exact.  (Packed f32x2 was measured
 //     slower, and ptxas 12.9 contracts mul.f32x2+add.f32x2 into FFMA2 even under -fmad=false.)  The chain runs
-//     continuously across the blocks of a launch.  The next block's input rows are staged HBM -> shared memory by TMA
-//     bulk copies (one per row, completing on an mbarrier), one block ahead.
+//     continuously across the blocks of a launch.
 //   * convolution warps, T = max(32, N/16) threads per stream (one warp at N = 512): left + i*right go through ONE
 //     complex N = 2B point Stockham FFT in shared memory (radix 8/4/2 in registers, two adjacent butterflies per thread
 //     so every shared-memory access is 128-bit), the frequency-domain delay line keeps that packed spectrum Z, and the
@@ -22,9 +23,11 @@
 //     with A = (G_L - i G_R)/2N, C = (G_L + i G_R)/2N, G_L = FFT(h_LSL + i h_LSR), G_R = FFT(h_RSL + i h_RSR):
 //     Re IFFT(W) is the left ear (LSL + RSL), Im IFFT(W) the right ear (LSR + RSR) (src/dsp/convolution.rs:229-230).
 //     One forward and one inverse FFT per block instead of the reference's four and four.  The products with the
-//     delay line's OLDER spectra (partitions 1..P-1) are accumulated before the wait for the block's EQ output.
-//   * the two roles are decoupled by named barriers over a 3-slot ring of filtered blocks, so the EQ of block t+1
-//     overlaps the convolution of block t, and are placed on the four scheduler partitions so that their loads balance.
+//     delay line's OLDER spectra (partitions 1..P-1) are accumulated before the wait for the block's EQ output.  With a
+//     single partition at N = 512 the last forward pass, the product and the first inverse pass run in registers.
+//   * the roles are decoupled by named barriers and mbarriers over a 3-slot ring of filtered blocks and the stage ring,
+//     so the staging of block t+3, the EQ of block t+1 and the convolution of block t overlap, and are placed on the
+//     four scheduler partitions so that their loads balance.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -420,14 +423,14 @@ __device__ __forceinline__ float df2t_step(float x, float& s1, float& s2, float 
     return out;
 }
 
-// EQ warp `w` of the CTA.  Lane (c, l): chain c = 6w + lane/5 is one (stream, channel) pair; the lane runs bands
-// A = 2l and B = 2l+1 of the 10-band cascade.  The chain is systolic in time:
-//     step s:  band A filters sample s - 4l      (input: lane l-1's band-B output of step s-3, by SHFL; lane 0: the input row)
+// EQ warp `w` of the CTA.  Lane l*6 + c: chain 6w + c is one (stream, channel) pair; the lane runs bands A = 2l and
+// B = 2l+1 of the 10-band cascade.  The chain is systolic in time:
+//     step s:  band A filters sample s - 4l      (input: lane l-1's band-B output of step s-3, by SHFL; l = 0: the input row)
 //              band B filters sample s - 4l - 1  (input: this lane's band-A output of step s-1)
-// so the last band (lane 4, B) runs 17 samples behind the first.  The shuffle of an output is issued the moment it
-// exists and consumed three steps later, so its 26-cycle latency never stalls the in-order warp, and the two bands of a
-// lane are two independent dependent-chains that cover each other's 4-cycle FP32 latency.  Every band's recurrence
-// is the strictly sequential reference recurrence (see df2t_step): bit-exact.
+// so the last band (l = 4, B) runs 17 samples behind the first.  A shuffled output is consumed three steps later, which
+// covers its latency (26 cycles alone, more while the convolution warps load the shared-memory pipe), and the two bands
+// of a lane are two independent dependent-chains that cover each other's 4-cycle FP32 latency.  Every band's
+// recurrence is the strictly sequential reference recurrence (see df2t_step): bit-exact.
 template <bool V> struct Flag { static constexpr bool value = V; };
 template <int N, int G>
 __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned char* smem, int stream0, int w) {
@@ -477,7 +480,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     }
 
     // Input rows: block t sits in stage buffer t % 3 once that buffer's mbarrier has completed its (t/3)-th phase.
-    // The copies are TMA bulk copies issued by a convolution warp (issue_input_stage below), three blocks ahead, so the
+    // The copies are TMA bulk copies issued by the staging warp (stager_warp_main), three blocks ahead, so the
     // EQ warps' critical path carries neither copy instructions nor a barrier for the buffer hand-over.  Only a ragged
     // last block (EQ-only mode) is loaded here, with plain guarded loads.
     uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
