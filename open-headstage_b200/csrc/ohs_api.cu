@@ -87,6 +87,11 @@ struct ohs_engine {
     cudaEvent_t ev_in[kPipe] = {}, ev_comp[kPipe] = {}, ev_out[kPipe] = {};
     size_t stage_frames = 0;
 
+    // time-batched long-response path: spectra in time order and frequency-domain products of one sub-launch
+    float2* d_zlin = nullptr;
+    float2* d_wlin = nullptr;
+    size_t zlin_blocks = 0;  // blocks per sub-launch the two buffers are sized for
+
     // FIFO adaptor (src/dsp/convolution.rs:141-182)
     std::vector<float> fifo_in, fifo_out;  // [row][cap]
     size_t fifo_cap = 0, fifo_in_len = 0, fifo_out_len = 0;
@@ -335,6 +340,78 @@ int pick_streams_per_cta(const ohs_engine* h) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kTimeBatch = 8;  // consecutive blocks a bin_conv_kernel thread accumulates (TB)
+
+template <int N> int launch_inverse(ohs_engine* h, float* d_out, int K, size_t row_stride) {
+    constexpr size_t smem = sizeof(float2) * 2 * padded_len(N);
+    static bool attr_set[64] = {};
+    const int dev = h->cfg.device;
+    if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !attr_set[dev]) {
+        OHS_CUDA(cudaFuncSetAttribute(inverse_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev] = true;
+    }
+    inverse_kernel<N><<<dim3(K, h->cfg.n_streams), fft_threads(N), smem, h->stream>>>(h->d_wlin, d_out, h->d_tw, h->d_stream_gain, K,
+                                                                                      (long long)row_stride);
+    OHS_CUDA(cudaGetLastError());
+    h->launches++;
+    return OHS_OK;
+}
+
+// Long responses, many blocks per call: per sub-launch of up to `zlin_blocks` blocks, (1) delay-line history into the
+// time-ordered buffer, (2) the render kernel in spectra-only mode (EQ, forward FFT, ring and buffer writes), (3) the
+// per-bin convolution along time, (4) the inverse transforms.  The delay-line ring, the overlap-save block and the EQ
+// state end up exactly where the block-by-block path leaves them, so the two can be mixed freely between calls.
+int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float* d_out, size_t row_stride) {
+    const size_t S = (size_t)h->cfg.n_streams, N = (size_t)h->N, hist = (size_t)h->pmax - 1;
+    const size_t budget = (size_t)2 << 30;
+    const size_t per_block = 2 * S * N * sizeof(float2), fixed = S * hist * N * sizeof(float2);
+    size_t kc = fixed < budget ? (budget - fixed) / per_block : 0;
+    kc = std::min<size_t>(std::min<size_t>(kc, 64), (size_t)p.n_blocks);
+    kc = kc / kTimeBatch * kTimeBatch;
+    if (kc < (size_t)kTimeBatch) return 1;  // does not fit the scratch budget: caller falls back to the block-by-block kernel
+    if (kc > h->zlin_blocks) {
+        if (h->d_zlin) OHS_CUDA(cudaFree(h->d_zlin));
+        if (h->d_wlin) OHS_CUDA(cudaFree(h->d_wlin));
+        h->d_zlin = h->d_wlin = nullptr; h->zlin_blocks = 0;
+        OHS_CUDA(cudaMalloc(&h->d_zlin, S * (hist + kc) * N * sizeof(float2)));
+        OHS_CUDA(cudaMalloc(&h->d_wlin, S * kc * N * sizeof(float2)));
+        h->zlin_blocks = kc;
+    }
+    const long long zstride = (long long)((hist + h->zlin_blocks) * N);
+    const int total = p.n_blocks;
+    for (int done = 0; done < total;) {
+        const int k = std::min<int>((int)h->zlin_blocks, total - done);
+        gather_history_kernel<<<dim3((unsigned)hist, (unsigned)S), 256, 0, h->stream>>>(h->d_fdl, h->d_zlin, (int)N, h->pmax, h->head, zstride);
+        OHS_CUDA(cudaGetLastError());
+        h->launches++;
+        p.in = d_in + (size_t)done * h->B; p.out = d_out + (size_t)done * h->B;
+        p.n_blocks = k; p.tail_frames = h->B; p.head = h->head;
+        p.zlin = h->d_zlin; p.zlin_stride = zstride; p.zlin_base = (int)hist; p.spectra_only = 1;
+        int rc = launch_render(h, p);
+        if (rc) return rc;
+        bin_conv_kernel<kTimeBatch><<<dim3((unsigned)((N / 2 + 127) / 128), (unsigned)((k + kTimeBatch - 1) / kTimeBatch), (unsigned)S), 128, 0, h->stream>>>(
+            h->d_zlin, h->d_wlin, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, zstride);
+        OHS_CUDA(cudaGetLastError());
+        h->launches++;
+        switch (h->N) {
+            case 128: rc = launch_inverse<128>(h, p.out, k, row_stride); break;
+            case 256: rc = launch_inverse<256>(h, p.out, k, row_stride); break;
+            case 512: rc = launch_inverse<512>(h, p.out, k, row_stride); break;
+            case 1024: rc = launch_inverse<1024>(h, p.out, k, row_stride); break;
+            case 2048: rc = launch_inverse<2048>(h, p.out, k, row_stride); break;
+            default: rc = fail(OHS_ERR_INVALID, "unsupported transform size %d", h->N);
+        }
+        if (rc) return rc;
+        h->head = (int)(((size_t)h->head + k) % (size_t)h->pmax);
+        done += k;
+    }
+    return OHS_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int ohs_abi_version(void) { return OHS_ABI_VERSION; }
@@ -452,7 +529,8 @@ int ohs_destroy(ohs_engine* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_stream_hrir, h->d_stream_eq, h->d_stream_gain, h->d_filt, h->d_set_parts, h->d_set_list, h->d_set_flags,
-                    h->d_fdl, h->d_prev, h->d_eqc, h->d_eqs, h->d_tw, h->d_ir, h->d_stage[0], h->d_stage[1], h->d_stage[2]};
+                    h->d_fdl, h->d_prev, h->d_eqc, h->d_eqs, h->d_tw, h->d_ir, h->d_stage[0], h->d_stage[1], h->d_stage[2],
+                    h->d_zlin, h->d_wlin};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < kPipe; ++i) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
@@ -652,11 +730,21 @@ int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_
     if (h->cfg.n_hrir_sets == 1 && h->N <= 512 && (size_t)h->h_set_parts[0] * h->N * sizeof(float4) <= 16 * 1024)
         p.filt_in_smem = h->h_set_parts[0];
     OHS_CUDA(cudaEventRecord(h->ev_k0, h->stream));
-    rc = launch_render(h, p);
-    if (rc) return rc;
+    // long responses over many blocks: convolve along time per bin instead of re-reading the delay line every block
+    bool batched = h->conv_enable && h->pmax >= 8 && p.n_blocks >= 2 * kTimeBatch;
+    if (const char* e = getenv("OHS_TIME_BATCH")) batched = batched && atoi(e) != 0;
+    if (batched) {
+        rc = process_time_batched(h, p, d_in, d_out, row_stride);
+        if (rc < 0) return rc;
+        batched = (rc == 0);
+    }
+    if (!batched) {
+        rc = launch_render(h, p);
+        if (rc) return rc;
+        if (h->conv_enable) h->head = (int)(((size_t)h->head + p.n_blocks) % (size_t)h->pmax);
+    }
     OHS_CUDA(cudaEventRecord(h->ev_k1, h->stream));
     h->timed = true;
-    if (h->conv_enable) h->head = (int)(((size_t)h->head + p.n_blocks) % (size_t)h->pmax);
     return OHS_OK;
 }
 

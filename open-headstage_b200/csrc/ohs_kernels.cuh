@@ -72,6 +72,10 @@ struct RenderParams {
     const float* eqc;           // [eq_set][kMaxBands][kEqCoefStride]
     float4* eqs;                // [stream][kMaxBands] {s1L, s1R, s2L, s2R}
     const float2* tw;           // [N] exp(-2*pi*i*m/N)
+    float2* zlin;               // time-batched mode (ohs_api.cu): [stream][zlin_base + K][N] spectra in time order, else null
+    long long zlin_stride;      // float2 per stream
+    int zlin_base;              // slot of this launch's block 0 (the pmax-1 slots before it hold the gathered history)
+    int spectra_only;           // time-batched mode: the convolution warps stop after the forward transform
     int pmax;
     int head;                   // ring slot of this launch's first block
     int n_bands;
@@ -827,7 +831,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
         for (int m = 0; m < kPairs; ++m)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[m][e] = make_float2(0.f, 0.f);
-        if constexpr (kTmaFilterPath) { if (tma_filters) {
+        if constexpr (kTmaFilterPath) { if (tma_filters && !p.spectra_only) {
             // Long impulse response shared by the CTA's streams (config 5): partition q's filter tile (16*N bytes, the
             // same for every stream) is brought into shared memory by ONE TMA bulk copy, double-buffered in the FFT
             // ping-pong buffers of streams 0 and 1 (idle until the forward FFT), while each thread keeps two
@@ -892,7 +896,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
                 }
             }
         } }
-        if (!tma_filters && valid && p.conv_enable && nparts > 1) {
+        if (!tma_filters && valid && p.conv_enable && nparts > 1 && !p.spectra_only) {
 #pragma unroll 1
             for (int m = 0; m < kPairs; ++m) {
                 const int k = 2 * (tid + m * T);
@@ -1003,14 +1007,19 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
         // ---- this block's spectrum: into the delay line, and its product with partition 0 on top of the history
         if (nparts > 1) {
             float4* dstz = reinterpret_cast<float4*>(fdl_s + (size_t)slot * N);
+            float4* dstl = p.zlin ? reinterpret_cast<float4*>(p.zlin + (size_t)s * p.zlin_stride + (size_t)(p.zlin_base + t) * N) : nullptr;
 #pragma unroll
             for (int e = 0; e < N / 2 / T; ++e) {
                 const int i = 2 * (tid + e * T);
                 float2 z0, z1;
                 zbuf.ld2(i, z0, z1);
                 dstz[i >> 1] = make_float4(z0.x, z0.y, z1.x, z1.y);
+                if (dstl) dstl[i >> 1] = make_float4(z0.x, z0.y, z1.x, z1.y);
             }
         }
+        // time-batched mode: the products and the inverse transforms of the whole launch follow in bin_conv_kernel and
+        // inverse_kernel
+        if (p.spectra_only) { stream_sync(); continue; }
         // partition 0's spectra come from the resident shared-memory copy (plain LDS: the address space is known at
         // compile time) or from global memory; one generic pointer for both would compile to generic loads
         auto mac_partition0 = [&](const float4* fq) {
@@ -1149,6 +1158,105 @@ __global__ void __launch_bounds__(SetupSmem<N>::T) setup_filters_kernel(const fl
         // even bins first, odd bins behind them: the layout the convolution warps' lane-contiguous loads want
         dst[(k & 1) * (N / 2) + (k >> 1)] = make_float4((l.x + r.y) * sc, (l.y - r.x) * sc, (l.x - r.y) * sc, (l.y + r.x) * sc);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Time-batched long responses (the offline per-bin pipeline).  The fused kernel re-reads every stream's
+// delay line (P-1 spectra of 8N bytes) for every block; for a launch of K blocks with a long response that is K(P-1)
+// spectrum reads per stream where K + P - 1 would do.  In this mode the render kernel only filters and transforms
+// (EQ, forward FFT, spectra into the delay-line ring AND into a buffer in time order), then per bin
+//     W_t[k] = sum_q  Z_{t-q}[k] A_q[k] + conj(Z_{t-q}[N-k]) C_q[k]
+// is a short convolution ALONG TIME: a thread owns a bin couple (k, N-k) of one stream and TB consecutive blocks,
+// keeps their TB accumulators and a sliding window of TB spectra in registers, and walks q once — one new spectrum
+// value and one filter tap loaded per step for TB*16 FMAs.  A third kernel runs the inverse transforms.
+// ---------------------------------------------------------------------------------------------------------------
+// history of the delay-line ring -> the first pmax-1 slots of the time-ordered buffer (slot pmax-1-q holds time -q)
+__global__ void gather_history_kernel(const float2* __restrict__ fdl, float2* __restrict__ zlin, int N, int pmax, int head,
+                                      long long zlin_stride) {
+    const int q = blockIdx.x + 1, s = blockIdx.y;
+    int sl = head - q; if (sl < 0) sl += pmax;
+    const float4* src = reinterpret_cast<const float4*>(fdl + ((size_t)s * pmax + sl) * N);
+    float4* dst = reinterpret_cast<float4*>(zlin + (size_t)s * zlin_stride + (size_t)(pmax - 1 - q) * N);
+    for (int i = threadIdx.x; i < N / 2; i += blockDim.x) dst[i] = src[i];
+}
+
+template <int TB>
+__global__ void __launch_bounds__(128) bin_conv_kernel(const float2* __restrict__ zlin, float2* __restrict__ wlin,
+                                                       const float4* __restrict__ filt, const int* __restrict__ stream_hrir,
+                                                       const int* __restrict__ set_parts, int N, int pmax, int K,
+                                                       long long zlin_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // couple index: bins (i, N-i); couple 0 is (0, N/2)
+    const int t0 = blockIdx.y * TB, s = blockIdx.z;
+    if (i >= N / 2) return;
+    const int k0 = i, k1 = i ? N - i : N / 2;
+    const int set = stream_hrir[s];
+    const int nparts = set_parts[set];
+    const float4* f = filt + (size_t)set * pmax * N;
+    const int f0i = (k0 & 1) * (N / 2) + (k0 >> 1), f1i = (k1 & 1) * (N / 2) + (k1 >> 1);   // even-bins-first table layout
+    const float2* z = zlin + (size_t)s * zlin_stride + (size_t)(pmax - 1) * N;   // z[tau * N + k]: time tau relative to block 0
+    float2 a0[TB], a1[TB], w0[TB], w1[TB];   // accumulators and spectrum window; window slot (tb - q) mod TB holds time t0+tb-q
+#pragma unroll
+    for (int tb = 0; tb < TB; ++tb) {
+        a0[tb] = make_float2(0.f, 0.f); a1[tb] = make_float2(0.f, 0.f);
+        const bool live = t0 + tb < K;
+        w0[tb] = live ? z[(size_t)(t0 + tb) * N + k0] : make_float2(0.f, 0.f);
+        w1[tb] = live ? z[(size_t)(t0 + tb) * N + k1] : make_float2(0.f, 0.f);
+    }
+    for (int q0 = 0; q0 < nparts; q0 += TB) {
+#pragma unroll
+        for (int r = 0; r < TB; ++r) {
+            const int q = q0 + r;
+            if (q < nparts) {
+                const float4 fa = f[(size_t)q * N + f0i], fb = f[(size_t)q * N + f1i];
+                // the spectrum that enters the window for step q+1 (time t0-q-1) replaces the one that leaves it
+                float2 n0 = make_float2(0.f, 0.f), n1 = n0;
+                if (q + 1 < nparts) {
+                    const long long tau = (long long)t0 - q - 1;
+                    n0 = z[tau * N + k0]; n1 = z[tau * N + k1];
+                }
+#pragma unroll
+                for (int tb = 0; tb < TB; ++tb) {
+                    const int ph = (tb - r + TB) % TB;
+                    mac_bin(a0[tb], w0[ph], i ? w1[ph] : w0[ph], fa);
+                    mac_bin(a1[tb], w1[ph], i ? w0[ph] : w1[ph], fb);
+                }
+                w0[(TB - 1 - r + TB) % TB] = n0;   // slot of time t0+TB-1-q, which step q+1 no longer needs
+                w1[(TB - 1 - r + TB) % TB] = n1;
+            }
+        }
+    }
+    float2* w = wlin + ((size_t)s * K) * N;
+#pragma unroll
+    for (int tb = 0; tb < TB; ++tb)
+        if (t0 + tb < K) { w[(size_t)(t0 + tb) * N + k0] = a0[tb]; w[(size_t)(t0 + tb) * N + k1] = a1[tb]; }
+}
+
+// first-pass loader of the inverse transform from global memory, with the swap of swap o FFT o swap
+struct SpectrumSwapLoad {
+    const float2* w;
+    __device__ __forceinline__ float2 ld(int i) const { const float2 v = w[i]; return make_float2(v.y, v.x); }
+    __device__ __forceinline__ void ld2(int i, float2& a, float2& b) const {
+        const float4 v = *reinterpret_cast<const float4*>(w + i);
+        a = make_float2(v.y, v.x); b = make_float2(v.w, v.z);
+    }
+};
+
+// one CTA per (block, stream): inverse transform of W_t, last B samples times gain to the output rows
+template <int N>
+__global__ void __launch_bounds__(SetupSmem<N>::T) inverse_kernel(const float2* __restrict__ wlin, float* __restrict__ out,
+                                                                const float2* __restrict__ tw_g, const float* __restrict__ stream_gain,
+                                                                int K, long long row_stride) {
+    constexpr int T = SetupSmem<N>::T, NP = SetupSmem<N>::NP, B = N / 2;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* b0 = reinterpret_cast<float2*>(smem);
+    float2* b1 = b0 + NP;
+    const int t = blockIdx.x, s = blockIdx.y;
+    const float2* w = wlin + ((size_t)s * K + t) * N;
+    float* out_l = out + ((size_t)s * 2) * row_stride;
+    float* out_r = out_l + row_stride;
+    auto sync = [&]() { __syncthreads(); };
+    fft_run<N, T>(threadIdx.x, tw_g, b0, b1, SpectrumSwapLoad{w},
+                  OutputStore{out_l + (size_t)t * B - B, out_r + (size_t)t * B - B, stream_gain[s], B}, sync, [&]() {});
 }
 
 // zero a stream's convolution history (delay line + overlap-save block) for streams bound to a flagged set, or all

@@ -530,3 +530,41 @@ def test_short_launches_every_path(n_blocks, mode):
     y = np.concatenate([e.process(x[:, :, :half]), e.process(x[:, :, half:])], axis=2) if half else e.process(x)
     err = float(np.max(np.abs(y - ref)))
     assert err <= TOL, err
+
+
+# ------------------------------------------------------------------------------------------------------------
+# long responses over many blocks: the time-batched path (per-bin convolution along time) against the oracle, against
+# the block-by-block kernel, and interleaved with it (the delay-line ring must end up identical)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("block,taps,n_streams,n_blocks", [(512, 5000, 3, 24), (1024, 9000, 2, 19), (128, 1500, 5, 40)])
+def test_time_batched_long_response(block, taps, n_streams, n_blocks, monkeypatch):
+    h = S.synthetic_hrir_set(taps, taps / 5.0, seed=21)
+    n = block * n_blocks
+    x = S.stream_inputs(n_streams, n, base_seed=1200)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL)
+    ref = oracle_render(x, block, h, coeffs, [1] * 10, 0.7)
+
+    def engine():
+        e = ohs.Engine(n_streams, block, taps)
+        e.set_hrir_set(h); e.eq_set_preset(S.EQ_PRESET_TYPICAL); e.set_eq_enable(True); e.set_gain(0.7)
+        return e
+
+    monkeypatch.setenv("OHS_TIME_BATCH", "1")
+    y_batched = engine().process(x)
+    assert float(np.max(np.abs(y_batched - ref))) <= TOL
+    monkeypatch.setenv("OHS_TIME_BATCH", "0")
+    y_blocks = engine().process(x)
+    assert float(np.max(np.abs(y_blocks - ref))) <= TOL
+    assert float(np.max(np.abs(y_blocks - y_batched))) <= 2e-6
+    # batched call, then block-by-block calls, then a batched call again on the same engine
+    e = engine()
+    cut1, cut2 = 16 * block, 16 * block + 2 * block
+    monkeypatch.setenv("OHS_TIME_BATCH", "1")
+    parts = [e.process(x[:, :, :cut1])]
+    monkeypatch.setenv("OHS_TIME_BATCH", "0")
+    parts.append(e.process(x[:, :, cut1:cut2]))
+    monkeypatch.setenv("OHS_TIME_BATCH", "1")
+    if cut2 < n:
+        parts.append(e.process(x[:, :, cut2:]))
+    y_mixed = np.concatenate(parts, axis=2)
+    assert float(np.max(np.abs(y_mixed - ref))) <= TOL
