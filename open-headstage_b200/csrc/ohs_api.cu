@@ -391,8 +391,16 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
         p.zlin = h->d_zlin; p.zlin_stride = zstride; p.zlin_base = (int)hist; p.spectra_only = 1;
         int rc = launch_render(h, p);
         if (rc) return rc;
-        bin_conv_kernel<kTimeBatch><<<dim3((unsigned)((N / 2 + 127) / 128), (unsigned)((k + kTimeBatch - 1) / kTimeBatch), (unsigned)S), 128, 0, h->stream>>>(
-            h->d_zlin, h->d_wlin, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, zstride);
+        {
+            const dim3 blk(128);
+            const unsigned gx = (unsigned)((N / 2 + 31) / 32), gz = (unsigned)((S + 3) / 4);
+            if (k >= 32)   // 16 blocks per thread: half the spectrum and filter traffic per FMA, 150 registers
+                bin_conv_kernel<16><<<dim3(gx, (unsigned)((k + 15) / 16), gz), blk, 16 * 128 * sizeof(float4), h->stream>>>(
+                    h->d_zlin, h->d_wlin, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride);
+            else
+                bin_conv_kernel<kTimeBatch><<<dim3(gx, (unsigned)((k + kTimeBatch - 1) / kTimeBatch), gz), blk, kTimeBatch * 128 * sizeof(float4), h->stream>>>(
+                    h->d_zlin, h->d_wlin, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride);
+        }
         OHS_CUDA(cudaGetLastError());
         h->launches++;
         switch (h->N) {

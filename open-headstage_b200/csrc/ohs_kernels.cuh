@@ -1180,50 +1180,76 @@ __global__ void gather_history_kernel(const float2* __restrict__ fdl, float2* __
     for (int i = threadIdx.x; i < N / 2; i += blockDim.x) dst[i] = src[i];
 }
 
+// Block = 4 warps = 4 streams x 32 bin couples: the four warps read the same filter taps (they hit in L1), each its own
+// stream's spectra (32 couples x 8 bytes contiguous per load).  The window of TB spectra lives in shared memory, one
+// 16-byte column entry per thread and slot (slot = time mod TB), so the step loop needs no unrolling over the
+// window's rotation: fully unrolled it is 90 KB of code and the kernel stalls on instruction fetch.
+template <int TB, bool kDc>
+__device__ __forceinline__ void bin_conv_steps(float2 (&a0)[TB], float2 (&a1)[TB], float4* win, const float4* __restrict__ f,
+                                               const float2* __restrict__ z, int N, int nparts, int t0, int f0i, int f1i,
+                                               int k0, int k1) {
+    // operands are loaded two steps ahead (a step is ~350 instructions, less than a loaded HBM round trip):
+    // fa/fb and (fa1, fb1, n0, n1) are the taps of steps q and q+1 and the spectrum that enters the window for step q+1
+    float4 fa = f[f0i], fb = f[f1i], fa1 = fa, fb1 = fb;
+    float2 n0 = make_float2(0.f, 0.f), n1 = n0;
+    if (1 < nparts) {
+        fa1 = f[(size_t)N + f0i]; fb1 = f[(size_t)N + f1i];
+        n0 = z[((long long)t0 - 1) * N + k0]; n1 = z[((long long)t0 - 1) * N + k1];
+    }
+#pragma unroll 1
+    for (int q = 0; q < nparts; ++q) {
+        float4 fa2 = fa1, fb2 = fb1;
+        float2 m0 = make_float2(0.f, 0.f), m1 = m0;
+        if (q + 2 < nparts) {
+            const long long tau = (long long)t0 - q - 2;   // the spectrum that enters the window for step q+2
+            fa2 = f[(size_t)(q + 2) * N + f0i]; fb2 = f[(size_t)(q + 2) * N + f1i];
+            m0 = z[tau * N + k0]; m1 = z[tau * N + k1];
+        }
+        const int rot = (TB - (q & (TB - 1))) & (TB - 1);   // slot of time t0+tb-q is (tb + rot) mod TB
+#pragma unroll
+        for (int tb = 0; tb < TB; ++tb) {
+            const float4 v = win[((tb + rot) & (TB - 1)) * 128];
+            const float2 u0 = make_float2(v.x, v.y), u1 = make_float2(v.z, v.w);
+            mac_bin(a0[tb], u0, kDc ? u0 : u1, fa);   // couple 0 = the two self-mirrored bins 0 and N/2
+            mac_bin(a1[tb], u1, kDc ? u1 : u0, fb);
+        }
+        win[((TB - 1 + rot) & (TB - 1)) * 128] = make_float4(n0.x, n0.y, n1.x, n1.y);   // time t0-q-1 replaces time t0+TB-1-q
+        fa = fa1; fb = fb1; fa1 = fa2; fb1 = fb2; n0 = m0; n1 = m1;
+    }
+}
+
 template <int TB>
-__global__ void __launch_bounds__(128) bin_conv_kernel(const float2* __restrict__ zlin, float2* __restrict__ wlin,
+__global__ void __launch_bounds__(128, 4) bin_conv_kernel(const float2* __restrict__ zlin, float2* __restrict__ wlin,
                                                        const float4* __restrict__ filt, const int* __restrict__ stream_hrir,
-                                                       const int* __restrict__ set_parts, int N, int pmax, int K,
+                                                       const int* __restrict__ set_parts, int N, int pmax, int K, int n_streams,
                                                        long long zlin_stride) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // couple index: bins (i, N-i); couple 0 is (0, N/2)
-    const int t0 = blockIdx.y * TB, s = blockIdx.z;
-    if (i >= N / 2) return;
+    static_assert((TB & (TB - 1)) == 0, "window slots are indexed modulo a power of two");
+    extern __shared__ __align__(16) unsigned char smem[];
+    float4* win = reinterpret_cast<float4*>(smem) + threadIdx.x;   // this thread's column: slot e at win[e * 128]
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31);   // couple index: bins (i, N-i); couple 0 is (0, N/2)
+    const int t0 = blockIdx.y * TB, s = blockIdx.z * 4 + (threadIdx.x >> 5);
+    if (i >= N / 2 || s >= n_streams) return;
     const int k0 = i, k1 = i ? N - i : N / 2;
     const int set = stream_hrir[s];
     const int nparts = set_parts[set];
     const float4* f = filt + (size_t)set * pmax * N;
     const int f0i = (k0 & 1) * (N / 2) + (k0 >> 1), f1i = (k1 & 1) * (N / 2) + (k1 >> 1);   // even-bins-first table layout
     const float2* z = zlin + (size_t)s * zlin_stride + (size_t)(pmax - 1) * N;   // z[tau * N + k]: time tau relative to block 0
-    float2 a0[TB], a1[TB], w0[TB], w1[TB];   // accumulators and spectrum window; window slot (tb - q) mod TB holds time t0+tb-q
+    float2 a0[TB], a1[TB];
 #pragma unroll
     for (int tb = 0; tb < TB; ++tb) {
         a0[tb] = make_float2(0.f, 0.f); a1[tb] = make_float2(0.f, 0.f);
         const bool live = t0 + tb < K;
-        w0[tb] = live ? z[(size_t)(t0 + tb) * N + k0] : make_float2(0.f, 0.f);
-        w1[tb] = live ? z[(size_t)(t0 + tb) * N + k1] : make_float2(0.f, 0.f);
+        const float2 v0 = live ? z[(size_t)(t0 + tb) * N + k0] : make_float2(0.f, 0.f);
+        const float2 v1 = live ? z[(size_t)(t0 + tb) * N + k1] : make_float2(0.f, 0.f);
+        win[tb * 128] = make_float4(v0.x, v0.y, v1.x, v1.y);
     }
-    for (int q0 = 0; q0 < nparts; q0 += TB) {
-#pragma unroll
-        for (int r = 0; r < TB; ++r) {
-            const int q = q0 + r;
-            if (q < nparts) {
-                const float4 fa = f[(size_t)q * N + f0i], fb = f[(size_t)q * N + f1i];
-                // the spectrum that enters the window for step q+1 (time t0-q-1) replaces the one that leaves it
-                float2 n0 = make_float2(0.f, 0.f), n1 = n0;
-                if (q + 1 < nparts) {
-                    const long long tau = (long long)t0 - q - 1;
-                    n0 = z[tau * N + k0]; n1 = z[tau * N + k1];
-                }
-#pragma unroll
-                for (int tb = 0; tb < TB; ++tb) {
-                    const int ph = (tb - r + TB) % TB;
-                    mac_bin(a0[tb], w0[ph], i ? w1[ph] : w0[ph], fa);
-                    mac_bin(a1[tb], w1[ph], i ? w0[ph] : w1[ph], fb);
-                }
-                w0[(TB - 1 - r + TB) % TB] = n0;   // slot of time t0+TB-1-q, which step q+1 no longer needs
-                w1[(TB - 1 - r + TB) % TB] = n1;
-            }
-        }
+    // couple 0 (bins 0 and N/2, each its own mirror) lives in lane 0 of the first couple group's warps only
+    if (blockIdx.x == 0) {
+        if (i == 0) bin_conv_steps<TB, true>(a0, a1, win, f, z, N, nparts, t0, f0i, f1i, k0, k1);
+        else bin_conv_steps<TB, false>(a0, a1, win, f, z, N, nparts, t0, f0i, f1i, k0, k1);
+    } else {
+        bin_conv_steps<TB, false>(a0, a1, win, f, z, N, nparts, t0, f0i, f1i, k0, k1);
     }
     float2* w = wlin + ((size_t)s * K) * N;
 #pragma unroll
