@@ -38,16 +38,14 @@
 namespace ohs {
 
 constexpr int kMaxBands = 10;
-// Two bands per lane: five lanes per chain, three EQ warps for seven streams (one per scheduler partition).  One band
-// per lane (ten lanes, five EQ warps) was measured too: two EQ warps then share a partition and the block time is the
-// same (844 k vs 852 k stream-s/s), for more issue slots.
-constexpr int kEqBandsPerLane = 2;
-constexpr int kEqGroup = kMaxBands / kEqBandsPerLane;  // lanes per (stream, channel) chain in an EQ warp
-constexpr int kEqChainsPerWarp = 32 / kEqGroup;
+// EQ warps run two bands per lane (five lanes per chain, six chains per warp) or one (ten lanes, three chains):
+// RenderSmem::kEqBpl.  For config 2's seven streams per CTA two bands per lane is the one that fits: with one band per
+// lane (five EQ warps) two EQ warps share a scheduler partition and the block time is the same (844 k vs 852 k
+// stream-s/s) for more issue slots.
 #ifndef OHS_EQ_WEIGHT
 #define OHS_EQ_WEIGHT 4
 #endif
-constexpr int kMaxG = 7;       // streams per CTA; their 2G chains of 5 lanes are spread over ceil(G/3) EQ warps
+constexpr int kMaxG = 7;       // streams per CTA
 constexpr int kEqSkew = 4;     // steps between neighbouring lanes of the systolic chain: a shuffled value is consumed 3 steps
                                // (~90 cycles) after it was sent.  8 was better while the FFT warps were heavier; on the final
                                // kernel 4 wins (948 k vs 908 k stream-s/s: fewer live registers, shorter fill and drain)
@@ -326,7 +324,13 @@ template <int N, int G> struct RenderSmem {
     static constexpr int B = N / 2;
     static constexpr int T = fft_threads(N);                 // convolution threads per stream (one warp at N <= 512)
     static constexpr int NP = padded_len(N);
-    static constexpr int kEqWarps = (2 * G + kEqChainsPerWarp - 1) / kEqChainsPerWarp;  // 3 (or 6) chains per EQ warp
+    // Bands per lane of the EQ warps.  2: five lanes per chain, six chains per warp (config 2: the issue slots of three
+    // warps are what the CTA can spare).  1: ten lanes per chain, three chains per warp, half the instructions and a
+    // single 12-cycle dependent chain per step — for the long blocks of N >= 1024, where a CTA holds few streams and
+    // the 1024-step sequential chain per block is the floor of the launch (config 5).
+    static constexpr int kEqBpl = (N >= 1024) ? 1 : 2;
+    static constexpr int kEqCpw = 32 / (kMaxBands / kEqBpl);   // chains per EQ warp: 6 or 3
+    static constexpr int kEqWarps = (2 * G + kEqCpw - 1) / kEqCpw;
     static constexpr int kEqThreads = 32 * kEqWarps;
     static constexpr int kConvWarps = G * T / 32;
     // Single-partition responses (config 2) at N = 512: the forward transform's last pass, the spectral product and the
@@ -359,7 +363,7 @@ template <int N, int G> struct RenderSmem {
             return pl;
         }
         int load[4] = {0, 0, 0, 0}, count[4] = {0, 0, 0, 0};
-        for (int w = 0; w < kEqWarps; ++w) { load[w & 3] += kEqWeight; count[w & 3] += 1; }
+        for (int w = 0; w < kEqWarps; ++w) { load[w & 3] += kEqWeight / (kEqBpl == 1 ? 2 : 1); count[w & 3] += 1; }
         for (int f = 0; f < kConvWarps; ++f) {
             int best = 3;
             for (int q = 3; q >= 0; --q) if (load[q] < load[best]) best = q;
@@ -440,14 +444,20 @@ template <int N, int G>
 __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned char* smem, int stream0, int w) {
     using SM = RenderSmem<N, G>;
     constexpr int B = SM::B;
-    constexpr int DL = (B >= 128) ? kEqSkew : 4;       // lane skew in steps = steps per unrolled iteration
+    constexpr int BPL = SM::kEqBpl;                    // bands per lane
+    constexpr int LPC = kMaxBands / BPL;               // lanes per chain
+    constexpr int CPW = SM::kEqCpw;                    // chains per warp
+    // lane skew in steps = steps per unrolled iteration.  One band per lane runs a step in half the time, too fast for
+    // a 3-step shuffle flight: skew 8.
+    constexpr int DL = (B >= 128) ? (BPL == 1 ? 8 : kEqSkew) : 4;
     constexpr int NQ = DL / 4;                         // float4 input loads per iteration
-    constexpr int BPL = kEqBandsPerLane;
-    constexpr int kOutLag = DL * (kEqGroup - 1) + (BPL - 1);  // steps the last band runs behind the first
+    constexpr int LL = DL - 1 + (BPL - 1);             // steps a lane runs behind its left neighbour: a shuffled value is used
+                                                       // DL-1 steps after it was sent, band B one step after band A
+    constexpr int kOutLag = LL * (LPC - 1) + (BPL - 1);  // steps the last band runs behind the first
     constexpr int kStoreU = (kOutLag + 3) % 4;         // the last lane completes an aligned group of 4 samples when u % 4 == kStoreU
     constexpr int kLagA = (kOutLag + DL - 1) / DL * DL;  // steps of a block during which the previous block is still being finished
     constexpr int kPending = 3 - kStoreU;              // outputs computed after the last group store of an iteration
-    static_assert((DL == 4 || DL == 8) && BPL == 2 && B % DL == 0 && B >= kLagA, "systolic loop layout");
+    static_assert((DL == 4 || DL == 8) && (BPL == 1 || BPL == 2) && B % DL == 0 && B >= kLagA, "systolic loop layout");
     constexpr int kCount = SM::kWorkers;
     float* ring_f = reinterpret_cast<float*>(smem + SM::kRingOff);
     float* stage = reinterpret_cast<float*>(smem + SM::kStageOff);
@@ -455,9 +465,9 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     const int lane = threadIdx.x & 31;
     // band-major lanes: lane = l * 6 + chain.  The six first lanes (input loads) and the six last lanes (output stores)
     // each fall into one quarter-warp, so a 128-bit shared-memory access of theirs is a single wavefront.
-    const int c_raw = kEqChainsPerWarp * w + lane % kEqChainsPerWarp;  // chain index in the CTA: 2*stream + channel
-    const int l = lane / kEqChainsPerWarp;
-    const bool chain_ok = (lane < kEqChainsPerWarp * kEqGroup) && (c_raw < 2 * G);
+    const int c_raw = CPW * w + lane % CPW;  // chain index in the CTA: 2*stream + channel
+    const int l = lane / CPW;
+    const bool chain_ok = (lane < CPW * LPC) && (c_raw < 2 * G);
     const int c = chain_ok ? c_raw : 0;
     const int g = c >> 1, ch = c & 1;
     const int s = stream0 + g;
@@ -469,7 +479,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     float bb0 = 0.f, bb1 = 0.f, bb2 = 0.f, ba1 = 0.f, ba2 = 0.f, bs1 = 0.f, bs2 = 0.f;
     bool en_a = false, en_b = false;
     const int band_a = BPL * l, band_b = BPL * l + 1;
-    const bool has_a = lane_valid && do_eq && band_a < p.n_bands, has_b = lane_valid && do_eq && band_b < p.n_bands;
+    const bool has_a = lane_valid && do_eq && band_a < p.n_bands, has_b = BPL == 2 && lane_valid && do_eq && band_b < p.n_bands;
     if (has_a) {
         const float* cf = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + band_a) * kEqCoefStride;
         ab0 = cf[0]; ab1 = cf[1]; ab2 = cf[2]; aa1 = cf[3]; aa2 = cf[4]; en_a = cf[5] != 0.f;
@@ -502,8 +512,8 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
         if (SM::kEqWarps > 1) bar_sync(kBarEq, SM::kEqThreads); else __syncwarp();
     };
 
-    const int src_lane = (l == 0) ? lane : lane - kEqChainsPerWarp;
-    const bool first = (l == 0), last = (l == kEqGroup - 1) && lane_valid;  // lanes of absent streams never store
+    const int src_lane = (l == 0) ? lane : lane - CPW;
+    const bool first = (l == 0), last = (l == LPC - 1) && lane_valid;  // lanes of absent streams never store
     // xsel[u]: band A's input at step u of the coming iteration, already chosen between the staged input sample (first
     // lane of a chain) and lane l-1's shuffled output.  The choice is made right behind the shuffle, an iteration ahead
     // of its use: ptxas gives a value whose only consumer lies behind the loop's back-edge the lowest priority and
@@ -528,16 +538,27 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     auto fast_iter = [&](auto sel, const In& in, const In& nx, int i0, float* dst) {
 #pragma unroll
         for (int u = 0; u < DL; ++u) {
-            const float xa = xsel[u];
-            const float y = df2t_step(ya_prev, bs1, bs2, bb0, bb1, bb2, ba1, ba2);   // band B on band A's previous output
-            ya_prev = df2t_step(xa, as1, as2, ab0, ab1, ab2, aa1, aa2);
-            const float r = __shfl_sync(0xffffffffu, y, src_lane);   // band A's input DL-1 steps from now
-            if (u == 0) xsel[DL - 1] = first ? in_at(in, DL - 1) : r;
-            else xsel[u - 1] = (decltype(sel)::value && first) ? in_at(nx, u - 1) : r;
-            if ((u & 3) == kStoreU && last)
-                *reinterpret_cast<float4*>(dst + (i0 + u - 3 - kOutLag)) =
-                    make_float4(yl[(u + DL - 3) % DL], yl[(u + DL - 2) % DL], yl[(u + DL - 1) % DL], y);
-            yl[u] = y;
+            if constexpr (BPL == 2) {
+                const float xa = xsel[u];
+                const float y = df2t_step(ya_prev, bs1, bs2, bb0, bb1, bb2, ba1, ba2);   // band B on band A's previous output
+                ya_prev = df2t_step(xa, as1, as2, ab0, ab1, ab2, aa1, aa2);
+                const float r = __shfl_sync(0xffffffffu, y, src_lane);   // band A's input DL-1 steps from now
+                if (u == 0) xsel[DL - 1] = first ? in_at(in, DL - 1) : r;
+                else xsel[u - 1] = (decltype(sel)::value && first) ? in_at(nx, u - 1) : r;
+                if ((u & 3) == kStoreU && last)
+                    *reinterpret_cast<float4*>(dst + (i0 + u - 3 - kOutLag)) =
+                        make_float4(yl[(u + DL - 3) % DL], yl[(u + DL - 2) % DL], yl[(u + DL - 1) % DL], y);
+                yl[u] = y;
+            } else {
+                const float y = df2t_step(xsel[u], as1, as2, ab0, ab1, ab2, aa1, aa2);
+                const float r = __shfl_sync(0xffffffffu, y, src_lane);
+                if (u == 0) xsel[DL - 1] = first ? in_at(in, DL - 1) : r;
+                else xsel[u - 1] = (decltype(sel)::value && first) ? in_at(nx, u - 1) : r;
+                if ((u & 3) == kStoreU && last)
+                    *reinterpret_cast<float4*>(dst + (i0 + u - 3 - kOutLag)) =
+                        make_float4(yl[(u + DL - 3) % DL], yl[(u + DL - 2) % DL], yl[(u + DL - 1) % DL], y);
+                yl[u] = y;
+            }
         }
     };
     // DL checked steps (pipeline fill and drain, ragged blocks, disabled bands): state and outputs are committed only
@@ -550,21 +571,34 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             const int na = na0 + u, nbi = na - 1;
             const bool act_a = lane_valid && na >= 0 && na < nb, act_b = lane_valid && nbi >= 0 && nbi < nb;
             const float xa = xsel[u];
-            float t1 = bs1, t2 = bs2;
-            float y = df2t_step(ya_prev, t1, t2, bb0, bb1, bb2, ba1, ba2);
-            const bool upd_b = act_b && en_b;
-            bs1 = upd_b ? t1 : bs1; bs2 = upd_b ? t2 : bs2;
-            y = upd_b ? y : ya_prev;
-            t1 = as1; t2 = as2;
-            float ya = df2t_step(xa, t1, t2, ab0, ab1, ab2, aa1, aa2);
-            const bool upd_a = act_a && en_a;
-            as1 = upd_a ? t1 : as1; as2 = upd_a ? t2 : as2;
-            ya_prev = upd_a ? ya : xa;
-            const float r = __shfl_sync(0xffffffffu, y, src_lane);
-            if (u == 0) xsel[DL - 1] = first ? in_at(in, DL - 1) : r;
-            else xsel[u - 1] = first ? in_at(nx, u - 1) : r;
-            if (act_b && last) dst0[nbi] = y;
-            yl[u] = y;
+            if constexpr (BPL == 2) {
+                float t1 = bs1, t2 = bs2;
+                float y = df2t_step(ya_prev, t1, t2, bb0, bb1, bb2, ba1, ba2);
+                const bool upd_b = act_b && en_b;
+                bs1 = upd_b ? t1 : bs1; bs2 = upd_b ? t2 : bs2;
+                y = upd_b ? y : ya_prev;
+                t1 = as1; t2 = as2;
+                float ya = df2t_step(xa, t1, t2, ab0, ab1, ab2, aa1, aa2);
+                const bool upd_a = act_a && en_a;
+                as1 = upd_a ? t1 : as1; as2 = upd_a ? t2 : as2;
+                ya_prev = upd_a ? ya : xa;
+                const float r = __shfl_sync(0xffffffffu, y, src_lane);
+                if (u == 0) xsel[DL - 1] = first ? in_at(in, DL - 1) : r;
+                else xsel[u - 1] = first ? in_at(nx, u - 1) : r;
+                if (act_b && last) dst0[nbi] = y;
+                yl[u] = y;
+            } else {
+                float t1 = as1, t2 = as2;
+                float y = df2t_step(xa, t1, t2, ab0, ab1, ab2, aa1, aa2);
+                const bool upd_a = act_a && en_a;
+                as1 = upd_a ? t1 : as1; as2 = upd_a ? t2 : as2;
+                y = upd_a ? y : xa;
+                const float r = __shfl_sync(0xffffffffu, y, src_lane);
+                if (u == 0) xsel[DL - 1] = first ? in_at(in, DL - 1) : r;
+                else xsel[u - 1] = first ? in_at(nx, u - 1) : r;
+                if (act_a && last) dst0[na] = y;
+                yl[u] = y;
+            }
         }
     };
     // input samples [i, i+DL) of a staged row: zeros past the end of the block ...
@@ -578,8 +612,18 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     // ... or, for the steady state's look-ahead loads, whatever follows: i <= B stays inside the stream's stage rows
     // (the right row, or the 4-float pad behind it), and what is read there is never used
     // Only a chain's first lane uses the samples: the load is predicated on it (6 active lanes, conflict-free rows).
-    static_assert(NQ == 1 && SM::kRowR >= B + 4 && SM::kStageStride >= SM::kRowR + B + 4, "look-ahead load of the last iteration reads the pad");
-    auto ld_fast = [&](In& in, const float* row, int i) { if (first) in.q[0] = *reinterpret_cast<const float4*>(row + i); };
+    // (NQ == 2 also reads the 16 bytes behind the pad: the next row, still inside the CTA's shared memory.)
+    static_assert(SM::kRowR >= B + 4 && SM::kStageStride >= SM::kRowR + B + 4, "look-ahead load of the last iteration reads the pad");
+    auto ld_fast = [&](In& in, const float* row, int i) {
+        if constexpr (NQ == 1) {
+            if (first) in.q[0] = *reinterpret_cast<const float4*>(row + i);
+        } else {
+            if (first) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) in.q[q] = *reinterpret_cast<const float4*>(row + i + 4 * q);
+            }
+        }
+    };
     // a block's first DL-1 inputs: taken from the staged row by the first lane, already in flight (shuffled) elsewhere
     auto seed_inputs = [&](const In& in0, bool keep) {
 #pragma unroll
@@ -587,11 +631,12 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     };
     // the stores of the first kLagA steps all belong to the previous block, all later ones to the block itself
     static_assert(kLagA - DL + kStoreU + (DL - 1 - kStoreU) / 4 * 4 - 3 - kOutLag < 0 && kLagA + kStoreU - 3 - kOutLag >= 0 &&
-                  (B - kLagA) % (2 * DL) == DL, "block = head iterations + pairs of iterations + one last iteration");
+                  B - kLagA >= DL, "block = head iterations + pairs of iterations + one or two last iterations");
+    constexpr bool kTwoLast = ((B - kLagA) / DL) % 2 == 0;
 
     // Every valid band filters and the launch is whole blocks: the chain runs continuously across the launch's blocks,
     // filling once at the start and draining once at the end.
-    const bool lane_fast = !lane_valid || !do_eq || (en_a && has_a && en_b && has_b);
+    const bool lane_fast = !lane_valid || !do_eq || (en_a && has_a && (BPL == 1 || (en_b && has_b)));
     const bool all_fast = __all_sync(0xffffffffu, lane_fast);
     const bool continuous = do_eq && p.tail_frames == B && (SM::kEqWarps > 1 ? __syncthreads_and_eq<SM::kEqThreads>(all_fast) : all_fast);
     float* ring_c = ring_f + (size_t)g * SM::kRingStride + ch * SM::kRingRowR;  // this chain's channel row of slot 0
@@ -608,7 +653,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             // during the first kLagA steps the first band starts block t while the last band finishes block t-1
             if (t == 0) {
 #pragma unroll 1
-                for (int i = 0; i < kLagA; i += DL) { b = ld_in(row, i + DL); checked_iter(a, b, i - DL * l, B, dcur); a = b; }
+                for (int i = 0; i < kLagA; i += DL) { b = ld_in(row, i + DL); checked_iter(a, b, i - LL * l, B, dcur); a = b; }
             } else {
                 float* dprev_end = ring_c + ((t + 2) % 3) * SM::kRingSlot + B;  // one past the previous block's row
 #pragma unroll 1
@@ -631,6 +676,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
                 fast_iter(SelNext{}, b, a, i + DL, dcur);
                 ld_fast(b, row, i + 3 * DL);
             }
+            if constexpr (kTwoLast) { fast_iter(SelNext{}, a, b, i, dcur); a = b; i += DL; }
             fast_iter(SelLater{}, a, a, i, dcur);
         }
         {
@@ -646,7 +692,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
             for (int q = 0; q < NQ; ++q) zero.q[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             seed_inputs(zero, true);
 #pragma unroll 1
-            for (int i = 0; i < kOutLag; i += DL) checked_iter(zero, zero, B + i - DL * l, B, dl);
+            for (int i = 0; i < kOutLag; i += DL) checked_iter(zero, zero, B + i - LL * l, B, dl);
             bar_arrive(kBarFull0 + ((p.n_blocks - 1) & 1), SM::kFullCount);
         }
     } else {
@@ -672,7 +718,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
                 xsel[DL - 1] = 0.f;
                 ya_prev = 0.f;
 #pragma unroll 1
-                for (int i = 0; i < nb + kOutLag; i += DL) { b = ld_in(row, i + DL); checked_iter(a, b, i - DL * l, nb, dst); a = b; }
+                for (int i = 0; i < nb + kOutLag; i += DL) { b = ld_in(row, i + DL); checked_iter(a, b, i - LL * l, nb, dst); a = b; }
             }
             bar_arrive(kBarFull0 + (t & 1), SM::kFullCount);
         }
