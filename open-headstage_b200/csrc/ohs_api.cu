@@ -394,11 +394,17 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
         {
             const dim3 blk(128);
             const unsigned gx = (unsigned)((N / 2 + 31) / 32), gz = (unsigned)((S + 3) / 4);
-            if (k >= 32)   // 16 blocks per thread: half the spectrum and filter traffic per FMA, 150 registers
-                bin_conv_kernel<16><<<dim3(gx, (unsigned)((k + 15) / 16), gz), blk, 16 * 128 * sizeof(float4), h->stream>>>(
+            static bool attr_set[64] = {};
+            const int dev = h->cfg.device;
+            if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+                OHS_CUDA(cudaFuncSetAttribute(bin_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 16 * 128 * sizeof(float4))));
+                attr_set[dev] = true;
+            }
+            if (k >= 32)   // 16 blocks per thread: half the spectrum and filter traffic per FMA
+                bin_conv_kernel<16><<<dim3(gx, (unsigned)((k + 15) / 16), gz), blk, 2 * 16 * 128 * sizeof(float4), h->stream>>>(
                     h->d_zlin, h->d_wlin, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride);
             else
-                bin_conv_kernel<kTimeBatch><<<dim3(gx, (unsigned)((k + kTimeBatch - 1) / kTimeBatch), gz), blk, kTimeBatch * 128 * sizeof(float4), h->stream>>>(
+                bin_conv_kernel<kTimeBatch><<<dim3(gx, (unsigned)((k + kTimeBatch - 1) / kTimeBatch), gz), blk, 2 * kTimeBatch * 128 * sizeof(float4), h->stream>>>(
                     h->d_zlin, h->d_wlin, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride);
         }
         OHS_CUDA(cudaGetLastError());

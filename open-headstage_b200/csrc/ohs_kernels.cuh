@@ -1252,20 +1252,25 @@ __device__ __forceinline__ void bin_conv_steps(float2 (&a0)[TB], float2 (&a1)[TB
             m0 = z[tau * N + k0]; m1 = z[tau * N + k1];
         }
         const int rot = (TB - (q & (TB - 1))) & (TB - 1);   // slot of time t0+tb-q is (tb + rot) mod TB
+        const float4* wrot = win + rot * 128;               // every slot is stored twice, TB slots apart: no wrap in the reads
 #pragma unroll
         for (int tb = 0; tb < TB; ++tb) {
-            const float4 v = win[((tb + rot) & (TB - 1)) * 128];
+            const float4 v = wrot[tb * 128];
             const float2 u0 = make_float2(v.x, v.y), u1 = make_float2(v.z, v.w);
             mac_bin(a0[tb], u0, kDc ? u0 : u1, fa);   // couple 0 = the two self-mirrored bins 0 and N/2
             mac_bin(a1[tb], u1, kDc ? u1 : u0, fb);
         }
-        win[((TB - 1 + rot) & (TB - 1)) * 128] = make_float4(n0.x, n0.y, n1.x, n1.y);   // time t0-q-1 replaces time t0+TB-1-q
+        {
+            const int e = (TB - 1 + rot) & (TB - 1);        // time t0-q-1 replaces time t0+TB-1-q
+            const float4 nv = make_float4(n0.x, n0.y, n1.x, n1.y);
+            win[e * 128] = nv; win[(e + TB) * 128] = nv;
+        }
         fa = fa1; fb = fb1; fa1 = fa2; fb1 = fb2; n0 = m0; n1 = m1;
     }
 }
 
 template <int TB>
-__global__ void __launch_bounds__(128, 4) bin_conv_kernel(const float2* __restrict__ zlin, float2* __restrict__ wlin,
+__global__ void __launch_bounds__(128, 3) bin_conv_kernel(const float2* __restrict__ zlin, float2* __restrict__ wlin,
                                                        const float4* __restrict__ filt, const int* __restrict__ stream_hrir,
                                                        const int* __restrict__ set_parts, int N, int pmax, int K, int n_streams,
                                                        long long zlin_stride) {
@@ -1289,6 +1294,7 @@ __global__ void __launch_bounds__(128, 4) bin_conv_kernel(const float2* __restri
         const float2 v0 = live ? z[(size_t)(t0 + tb) * N + k0] : make_float2(0.f, 0.f);
         const float2 v1 = live ? z[(size_t)(t0 + tb) * N + k1] : make_float2(0.f, 0.f);
         win[tb * 128] = make_float4(v0.x, v0.y, v1.x, v1.y);
+        win[(tb + TB) * 128] = make_float4(v0.x, v0.y, v1.x, v1.y);
     }
     // couple 0 (bins 0 and N/2, each its own mirror) lives in lane 0 of the first couple group's warps only
     if (blockIdx.x == 0) {
