@@ -133,7 +133,10 @@ int ohs_conv_reset(ohs_engine* h);
  * src/dsp/parametric_eq.rs:166 + gain loop src/lib.rs:1202-1207).  n_frames must be a multiple of B: whole engine
  * blocks, i.e. the zero-latency case of the reference's FIFO (host block = multiple of BLOCK_SIZE).
  * in == out (in place) is allowed.  row_stride = frames between consecutive (stream, channel) rows (>= n_frames).
- * Device flavour: pointers are device memory on cfg.device; the call only enqueues on the engine's stream. */
+ * Device flavour: pointers are device memory on cfg.device; the call only enqueues on the engine's stream.
+ * Long responses (>= 8 partitions) rendered >= 16 blocks per call take a time-batched route (spectra first, then a
+ * per-bin convolution along time, then the inverse transforms; up to 2 GiB of scratch on first use) with the same
+ * results within round-off and the same state afterwards; the environment variable OHS_TIME_BATCH=0 disables it. */
 int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_frames, size_t row_stride);
 /* Host flavour: pointers are host memory (pinned memory from ohs_host_alloc gives full PCIe speed); the call
  * stages time chunks through HBM with copies overlapped against the kernels and returns when `out` is complete. */
