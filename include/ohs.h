@@ -134,7 +134,7 @@ int ohs_conv_reset(ohs_engine* h);
  * blocks, i.e. the zero-latency case of the reference's FIFO (host block = multiple of BLOCK_SIZE).
  * in == out (in place) is allowed.  row_stride = frames between consecutive (stream, channel) rows (>= n_frames).
  * Device flavour: pointers are device memory on cfg.device; the call only enqueues on the engine's stream.
- * Long responses (>= 8 partitions) rendered >= 16 blocks per call take a time-batched route (spectra first, then a
+ * Long responses (>= 8 partitions) rendered >= 8 blocks per call take a time-batched route (spectra first, then a
  * per-bin convolution along time, then the inverse transforms; up to 2 GiB of scratch on first use) with the same
  * results within round-off and the same state afterwards; the environment variable OHS_TIME_BATCH=0 disables it. */
 int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_frames, size_t row_stride);

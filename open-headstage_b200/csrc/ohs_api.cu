@@ -369,7 +369,6 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
     const size_t per_block = 2 * S * N * sizeof(float2), fixed = S * hist * N * sizeof(float2);
     size_t kc = fixed < budget ? (budget - fixed) / per_block : 0;
     kc = std::min<size_t>(std::min<size_t>(kc, 64), (size_t)p.n_blocks);
-    kc = kc / kTimeBatch * kTimeBatch;
     if (kc < (size_t)kTimeBatch) return 1;  // does not fit the scratch budget: caller falls back to the block-by-block kernel
     if (kc > h->zlin_blocks) {
         if (h->d_zlin) OHS_CUDA(cudaFree(h->d_zlin));
@@ -745,7 +744,7 @@ int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_
         p.filt_in_smem = h->h_set_parts[0];
     OHS_CUDA(cudaEventRecord(h->ev_k0, h->stream));
     // long responses over many blocks: convolve along time per bin instead of re-reading the delay line every block
-    bool batched = h->conv_enable && h->pmax >= 8 && p.n_blocks >= 2 * kTimeBatch;
+    bool batched = h->conv_enable && h->pmax >= 8 && p.n_blocks >= kTimeBatch;
     if (const char* e = getenv("OHS_TIME_BATCH")) batched = batched && atoi(e) != 0;
     if (batched) {
         rc = process_time_batched(h, p, d_in, d_out, row_stride);

@@ -60,5 +60,5 @@ if __name__ == "__main__":
         for k in (1, 16, 128):
             run("cfg3 (one GPU's 8192 streams)", 8192, 128, 512, 48000.0, 80.0, k)
     if "cfg5" in which:
-        for k in (1, 8, 16, 32, 64, 128):
+        for k in (1, 4, 8, 16, 32, 64, 128):
             run("cfg5 (one GPU's 256 streams)", 256, 1024, 48000, 96000.0, 0.15 * 96000.0, k)
