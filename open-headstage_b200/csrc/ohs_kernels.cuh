@@ -992,7 +992,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
             continue;
         }
         if constexpr (SM::kFusedMac) {
-            if (nparts == 1) {
+            if (nparts == 1 && !p.spectra_only) {
                 // ---- single partition: forward passes 1 and 2 through shared memory; then the last forward pass, the
                 // spectral product and the first inverse pass in registers.  The last pass's butterfly i produces the
                 // bins i + q*NB (q < R), exactly the inputs of the inverse transform's first-pass butterfly i, and the
@@ -1051,15 +1051,17 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
                       [&]() { if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount); });
         stream_sync();
         // ---- this block's spectrum: into the delay line, and its product with partition 0 on top of the history
-        if (nparts > 1) {
-            float4* dstz = reinterpret_cast<float4*>(fdl_s + (size_t)slot * N);
+        if (nparts > 1 || p.zlin) {
+            // (a single-partition stream keeps no delay line, but in time-batched mode its spectrum still goes to the
+            // time-ordered buffer: the per-bin kernel computes every stream's products)
+            float4* dstz = nparts > 1 ? reinterpret_cast<float4*>(fdl_s + (size_t)slot * N) : nullptr;
             float4* dstl = p.zlin ? reinterpret_cast<float4*>(p.zlin + (size_t)s * p.zlin_stride + (size_t)(p.zlin_base + t) * N) : nullptr;
 #pragma unroll
             for (int e = 0; e < N / 2 / T; ++e) {
                 const int i = 2 * (tid + e * T);
                 float2 z0, z1;
                 zbuf.ld2(i, z0, z1);
-                dstz[i >> 1] = make_float4(z0.x, z0.y, z1.x, z1.y);
+                if (dstz) dstz[i >> 1] = make_float4(z0.x, z0.y, z1.x, z1.y);
                 if (dstl) dstl[i >> 1] = make_float4(z0.x, z0.y, z1.x, z1.y);
             }
         }

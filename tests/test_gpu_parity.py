@@ -569,3 +569,23 @@ def test_time_batched_long_response(block, taps, n_streams, n_blocks, monkeypatc
         parts.append(e.process(x[:, :, cut2:]))
     y_mixed = np.concatenate(parts, axis=2)
     assert float(np.max(np.abs(y_mixed - ref))) <= TOL
+
+
+def test_time_batched_mixed_hrir_sets(monkeypatch):
+    """Two HRIR sets on one engine, a long one (10 partitions) and a single-partition one, streams bound alternately:
+    the time-batched route renders both kinds (a single-partition stream has no delay line of its own)."""
+    block, n_streams, n_blocks = 512, 5, 20
+    h_long = S.synthetic_hrir_set(5000, 900.0, seed=31)
+    h_short = S.synthetic_hrir_set(300, 60.0, seed=32)
+    x = S.stream_inputs(n_streams, block * n_blocks, base_seed=1300)
+    refs = {0: oracle_render(x, block, h_long), 1: oracle_render(x, block, h_short)}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("OHS_TIME_BATCH", mode)
+        e = ohs.Engine(n_streams, block, 5000, n_bands=0, n_hrir_sets=2)
+        e.set_hrir_set(h_long, hrir_set=0); e.set_hrir_set(h_short, hrir_set=1)
+        for s in range(n_streams):
+            e.bind_stream_hrir(s, s % 2)
+        y = e.process(x)
+        for s in range(n_streams):
+            err = float(np.max(np.abs(y[s] - refs[s % 2][s])))
+            assert err <= TOL, (mode, s, err)
