@@ -537,7 +537,7 @@ def test_short_launches_every_path(n_blocks, mode):
 # the block-by-block kernel, and interleaved with it (the delay-line ring must end up identical)
 # ------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("block,taps,n_streams,n_blocks", [(512, 5000, 3, 24), (1024, 9000, 2, 19), (128, 1500, 5, 40), (128, 1100, 3, 150),
-                                                           (256, 2100, 9, 11)])
+                                                           (256, 2100, 9, 11), (64, 600, 2, 17)])
 def test_time_batched_long_response(block, taps, n_streams, n_blocks, monkeypatch):
     h = S.synthetic_hrir_set(taps, taps / 5.0, seed=21)
     n = block * n_blocks
