@@ -401,8 +401,7 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
             }
             // 16 blocks per thread (half the spectrum and filter traffic per FMA) from 16 blocks per sub-launch on:
             // measured faster than 8 at K = 16 (0.529 vs 0.560 ms), 32, 64 and 128 on config 5
-            bool tb16 = k >= 16;
-            if (const char* e = getenv("OHS_BINCONV_TB")) tb16 = atoi(e) == 16;   // A/B switch
+            const bool tb16 = k >= 16;
             if (tb16)
                 bin_conv_kernel<16><<<dim3(gx, (unsigned)((k + 15) / 16), gz), blk, 2 * 16 * 128 * sizeof(float4), h->stream>>>(
                     h->d_zlin, h->d_wlin, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride);
