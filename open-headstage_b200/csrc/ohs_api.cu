@@ -747,7 +747,7 @@ int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_
         p.filt_in_smem = h->h_set_parts[0];
     OHS_CUDA(cudaEventRecord(h->ev_k0, h->stream));
     // long responses over many blocks: convolve along time per bin instead of re-reading the delay line every block
-    bool batched = h->conv_enable && h->pmax >= 8 && p.n_blocks >= kTimeBatch;
+    bool batched = h->conv_enable && h->pmax >= 8 && p.n_blocks >= kTimeBatch && h->cfg.n_streams <= 65535;  // (grid.y = stream)
     if (const char* e = getenv("OHS_TIME_BATCH")) batched = batched && atoi(e) != 0;
     if (batched) {
         rc = process_time_batched(h, p, d_in, d_out, row_stride);
