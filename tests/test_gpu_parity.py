@@ -283,8 +283,12 @@ def test_config2_3_chain_parity(cfg, n_streams, seconds):
     assert err <= TOL, err
 
 
-def test_config5_long_brir_parity():
-    """cfg 5: 48 000-tap BRIR per path, partition 1024, 96 kHz (47 partitions); 3 streams x 60 blocks."""
+@pytest.mark.parametrize("time_batch", ["1", "0"])
+def test_config5_long_brir_parity(time_batch, monkeypatch):
+    """cfg 5: 48 000-tap BRIR per path, partition 1024, 96 kHz (47 partitions); 3 streams x 60 blocks, through the
+    time-batched route and through the block-by-block kernel (TMA filter tiles: 3 streams = two per CTA)."""
+    monkeypatch.setenv("OHS_TIME_BATCH", time_batch)
+    monkeypatch.setenv("OHS_STREAMS_PER_CTA", "2")
     c = S.CONFIGS[5]
     h = S.synthetic_hrir_set(c["taps"], c["decay"])
     n = 1024 * 60
