@@ -42,6 +42,9 @@ def test_library_is_sm100a_native_code():
     assert "sm_100a" in elf
     sass = subprocess.run([cuobjdump, "-sass", lib_path], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass    # TMA bulk copies (cp.async.bulk) stage the input rows into shared memory
+    for kernel in ("render_kernel", "setup_filters_kernel", "bin_conv_kernel", "inverse_kernel", "gather_history_kernel",
+                   "clear_history_kernel", "mix_streams_kernel"):
+        assert kernel in sass, kernel   # every kernel of the path is in the shipped library
     assert "SYNCS" in sass     # ... completing on mbarriers
     assert "SHFL.IDX" in sass  # the band-systolic EQ chain
     assert "BAR.ARV" in sass or "BAR.ARRIVE" in sass or "BAR.SYNC" in sass  # named-barrier producer/consumer hand-off
