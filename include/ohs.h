@@ -24,6 +24,9 @@
  *   - one handle = one CUDA stream; a handle is not re-entrant (the reference API is `&mut self`); distinct
  *     handles are independent.
  *   - there is no CPU fallback: if no CUDA device is usable, ohs_create fails.
+ *   - the environment is read once, in ohs_create: OHS_STREAMS_PER_CTA (1..7, which render-kernel instantiation the
+ *     handle uses; default: chosen from n_streams and the SM count), OHS_TIME_BATCH (0 = ohs_set_time_batch(h, 0)),
+ *     OHS_STAGE_MB (staging chunk of the host-pointer path, default 24), OHS_PDL (0 = no programmatic dependent launches).
  */
 #ifndef OHS_H
 #define OHS_H
@@ -35,7 +38,7 @@
 extern "C" {
 #endif
 
-#define OHS_ABI_VERSION 1
+#define OHS_ABI_VERSION 2
 
 typedef enum ohs_status {
     OHS_OK = 0,
@@ -116,8 +119,9 @@ int ohs_eq_set_band(ohs_engine* h, int eq_set, int band, const float coeffs[5], 
 int ohs_bind_stream_eq(ohs_engine* h, int stream, int eq_set);
 /* StereoParametricEQ::reset_all_bands_state (src/dsp/parametric_eq.rs:181-188; Plugin::reset src/lib.rs:1152-1154). */
 int ohs_eq_reset(ohs_engine* h);
-/* StereoParametricEQ::calculate_frequency_response (src/dsp/parametric_eq.rs:191-209), enabled bands of `eq_set`. */
-int ohs_eq_frequency_response(ohs_engine* h, int eq_set, const float* freqs, float* out, size_t n);
+/* StereoParametricEQ::calculate_frequency_response(sample_rate, frequencies) (src/dsp/parametric_eq.rs:191-209):
+ * |product over the enabled bands of `eq_set` of H(e^{j 2 pi f / sample_rate})|; sample_rate <= 0 means cfg.sample_rate. */
+int ohs_eq_frequency_response(ohs_engine* h, int eq_set, float sample_rate, const float* freqs, float* out, size_t n);
 
 /* ---- chain switches (Plugin::process, src/lib.rs:1169-1207) ------------------------------------------------- */
 int ohs_set_eq_enable(ohs_engine* h, int enable);          /* params.eq_enable (:1179) */
@@ -126,6 +130,15 @@ int ohs_set_bypass(ohs_engine* h, int bypass);             /* params.master_bypa
 int ohs_set_gain(ohs_engine* h, int stream, float gain);   /* output_gain, one value per call (:1202-1207); stream or OHS_ALL */
 /* Clears convolution history (as a fresh ConvolutionEngine with the same IRs would have). */
 int ohs_conv_reset(ohs_engine* h);
+/* 0 keeps long responses on the block-by-block kernel (see ohs_process_device); default 1. */
+int ohs_set_time_batch(ohs_engine* h, int enable);
+/* Streams each CTA of the render kernel carries for this handle (which instantiation render_kernel<2*block, G> runs). */
+int ohs_streams_per_cta(ohs_engine* h, int* out);
+/* Set-up that would otherwise happen lazily inside the first process call of that size: uploads pending set_ir /
+ * EQ / binding work and allocates the scratch (time-batched route) and, for host_io != 0, the staging buffers that
+ * calls of n_frames frames need.  Optional; lets a caller keep allocation out of a timed or real-time region, the
+ * way Plugin::initialize (src/lib.rs:1124-1150) allocates before process() runs. */
+int ohs_prepare(ohs_engine* h, size_t n_frames, int host_io);
 
 /* ---- processing ------------------------------------------------------------------------------------------- */
 /* The per-block process call: EQ (if enabled) -> convolution -> gain for every stream, n_frames frames each
@@ -135,8 +148,9 @@ int ohs_conv_reset(ohs_engine* h);
  * in == out (in place) is allowed.  row_stride = frames between consecutive (stream, channel) rows (>= n_frames).
  * Device flavour: pointers are device memory on cfg.device; the call only enqueues on the engine's stream.
  * Long responses (>= 8 partitions) rendered >= 8 blocks per call take a time-batched route (spectra first, then a
- * per-bin convolution along time, then the inverse transforms; up to 2 GiB of scratch on first use) with the same
- * results within round-off and the same state afterwards; the environment variable OHS_TIME_BATCH=0 disables it. */
+ * per-bin convolution along time, then the inverse transforms; up to 2 GiB of scratch, allocated on first use or by
+ * ohs_prepare) with the same results within round-off and the same state afterwards; ohs_set_time_batch(h, 0)
+ * disables it. */
 int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_frames, size_t row_stride);
 /* Host flavour: pointers are host memory (pinned memory from ohs_host_alloc gives full PCIe speed); the call
  * stages time chunks through HBM with copies overlapped against the kernels and returns when `out` is complete. */
@@ -164,7 +178,14 @@ int ohs_mix_device(ohs_engine* h, const float* d_in, float* d_bus, size_t n_fram
 int ohs_host_alloc(void** p, size_t bytes);
 int ohs_host_free(void* p);
 
-/* ---- state export / import (chunked offline renders resume bit-exactly) ---------------------- */
+/* Debug builds only (-DOHS_TRACE): d_stamps[CTA][16] receives clock64 stamps of the render kernel's milestones
+ * (tools/trace_k1.py); a regular build returns OHS_ERR_INVALID. */
+int ohs_debug_trace(ohs_engine* h, unsigned long long* d_stamps);
+
+/* ---- state export / import (chunked offline renders resume bit-exactly) ----------------------
+ * The blob holds a self-describing header (geometry, ring head, byte count), the delay line, the overlap-save blocks,
+ * the biquad states and whatever ohs_process_fifo has queued; import rejects a blob whose geometry, size or ring
+ * head does not match this engine.  ohs_state_bytes is the size an export would need NOW (it grows with the FIFO). */
 int ohs_state_bytes(ohs_engine* h, size_t* bytes);
 int ohs_state_export(ohs_engine* h, void* host_buf, size_t bytes);
 int ohs_state_import(ohs_engine* h, const void* host_buf, size_t bytes);

@@ -8,14 +8,18 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.environ.get("OHS_LIB_OVERRIDE") or os.path.join(HERE, "libohs_cuda.so")  # override: A/B experiments only
-SOURCES = [os.path.join(HERE, "csrc", "ohs_api.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", "ohs_kernels.cuh"), os.path.join(ROOT, "include", "ohs.h")]
+CSRC = os.path.join(HERE, "csrc")
+RENDER_SIZES = (128, 256, 512, 1024, 2048)   # transform sizes N = 2 * block; one object of csrc/ohs_render.cu per size
+SOURCES = [os.path.join(CSRC, "ohs_api.cu"), os.path.join(CSRC, "ohs_render.cu")]
+DEPS = SOURCES + [os.path.join(CSRC, "ohs_kernels.cuh"), os.path.join(CSRC, "ohs_aux_kernels.cuh"), os.path.join(CSRC, "ohs_launch.h"),
+                  os.path.join(ROOT, "include", "ohs.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     # no -use_fast_math: denormals are kept (-ftz=false) and division/sqrt stay IEEE, as on the reference's CPU path
 ]
+EXTRA_FLAGS = os.environ.get("OHS_NVCC_EXTRA", "").split()   # e.g. -DOHS_TRACE for the instrumented A/B library
 
 
 def nvcc_path() -> str:
@@ -32,7 +36,7 @@ def _source_hash() -> str:
     for d in DEPS:
         with open(d, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -50,24 +54,42 @@ def is_stale() -> bool:
         return True
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if force or is_stale():
-        tmp = LIB + ".tmp.%d" % os.getpid()
-        cmd = [nvcc_path(), *NVCC_FLAGS, "-o", tmp, *SOURCES]
-        if verbose:
-            cmd.insert(1, "-Xptxas")
-            cmd.insert(2, "-v")
-        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
-        if verbose or r.returncode:
-            print(r.stdout + r.stderr)
-        if r.returncode:
-            if os.path.exists(tmp):
-                os.unlink(tmp)
-            raise RuntimeError("nvcc failed building libohs_cuda.so")
-        os.replace(tmp, LIB)  # atomic: concurrent ranks never see a half-written library
-        with open(LIB + ".srchash", "w") as f:
-            f.write(_source_hash())
-    return LIB
+def _run(cmd, verbose):
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(" ".join(cmd))
+        print(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed building libohs_cuda.so")
+
+
+def build_library(force: bool = False, verbose: bool = False, out: str | None = None, extra_flags=()) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a: ohs_api.cu and one object of ohs_render.cu per transform size,
+    compiled in parallel, linked into one shared library."""
+    lib = out or LIB
+    if not (force or out or is_stale()):
+        return lib
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = nvcc_path()
+    objdir = os.path.join(HERE, "build", "obj.%d" % os.getpid())
+    os.makedirs(objdir, exist_ok=True)
+    flags = NVCC_FLAGS + EXTRA_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+    jobs = [([nvcc, *flags, "-c", SOURCES[0], "-o", os.path.join(objdir, "ohs_api.o")])]
+    for n in RENDER_SIZES:
+        jobs.append([nvcc, *flags, "-DOHS_RENDER_N=%d" % n, "-c", SOURCES[1], "-o", os.path.join(objdir, "ohs_render_%d.o" % n)])
+    try:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            list(ex.map(lambda c: _run(c, verbose), jobs))
+        tmp = lib + ".tmp.%d" % os.getpid()
+        _run([nvcc, "-shared", "-o", tmp, *[j[-1] for j in jobs], "-ldl"], verbose)
+        os.replace(tmp, lib)  # atomic: concurrent ranks never see a half-written library
+        if not out:
+            with open(LIB + ".srchash", "w") as f:
+                f.write(_source_hash())
+    finally:
+        shutil.rmtree(objdir, ignore_errors=True)
+    return lib
 
 
 HOST_TEST_BIN = os.path.join(HERE, "host", "ref_unit_tests")

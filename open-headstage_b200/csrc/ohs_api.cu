@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -18,7 +19,8 @@
 #include <string>
 #include <vector>
 
-#include "ohs_kernels.cuh"
+#include "ohs_aux_kernels.cuh"
+#include "ohs_launch.h"
 
 namespace {
 
@@ -81,6 +83,12 @@ struct ohs_engine {
     int head = 0;
     int eq_enable = 0, conv_enable = 1, bypass = 0;
     uint64_t launches = 0;
+    // tuning switches, read from the environment ONCE at ohs_create (and settable through the API afterwards)
+    int time_batch = 1;            // OHS_TIME_BATCH / ohs_set_time_batch: 0 keeps long responses on the block-by-block kernel
+    size_t stage_bytes = (size_t)24 << 20;  // OHS_STAGE_MB: staging chunk of the host-pointer path
+    bool dependent_launch = true;  // OHS_PDL=0 switches programmatic dependent launches off
+    unsigned long long* d_trace = nullptr;  // ohs_debug_trace (OHS_TRACE builds)
+    std::vector<float> h_ir_padded;         // [set][4][pmax*B] host mirror of d_ir, uploaded in one copy per commit
 
     // host-pointer path
     float* d_stage[kPipe] = {nullptr, nullptr, nullptr};
@@ -101,75 +109,49 @@ namespace {
 
 using namespace ohs;
 
-template <int N, int G> int launch_render_ng(ohs_engine* h, const RenderParams& p) {
-    using SM = RenderSmem<N, G>;
-    static bool attr_set[64] = {};
-    int dev = h->cfg.device;
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        OHS_CUDA(cudaFuncSetAttribute(render_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kBytes));
-        OHS_CUDA(cudaFuncSetAttribute(render_kernel<N, G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_set[dev] = true;
+int launch_render(ohs_engine* h, const RenderParams& p, int first_stream = 0) {
+    RenderLaunch L{h->G, h->cfg.device, h->stream, first_stream, h->dependent_launch};
+    RenderParams q = p;
+    q.trace = h->d_trace;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (h->N) {
+        case 128: e = render_launch_128(L, q); break;
+        case 256: e = render_launch_256(L, q); break;
+        case 512: e = render_launch_512(L, q); break;
+        case 1024: e = render_launch_1024(L, q); break;
+        case 2048: e = render_launch_2048(L, q); break;
+        default: return fail(OHS_ERR_INVALID, "unsupported block size %d", h->B);
     }
-    const int grid = (p.n_streams + G - 1) / G;
-    render_kernel<N, G><<<grid, SM::kThreads, SM::kBytes, h->stream>>>(p);
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return fail(OHS_ERR_INVALID, "%d streams per CTA do not fit for block %d", h->G, h->B); }
+    if (e != cudaSuccess) return fail(OHS_ERR_CUDA, "render kernel launch failed: %s", cudaGetErrorString(e));
     OHS_CUDA(cudaGetLastError());
     h->launches++;
     return OHS_OK;
 }
 
-template <int N, int G> int launch_render_if_fits(ohs_engine* h, const RenderParams& p) {
-    if constexpr (RenderSmem<N, G>::kFits) return launch_render_ng<N, G>(h, p);
-    else return fail(OHS_ERR_INVALID, "%d streams per CTA do not fit for block %d", G, N / 2);
-}
-
-template <int N> int launch_render_n(ohs_engine* h, const RenderParams& p) {
-    switch (h->G) {
-        case 1: return launch_render_if_fits<N, 1>(h, p);
-        case 2: return launch_render_if_fits<N, 2>(h, p);
-        case 3: return launch_render_if_fits<N, 3>(h, p);
-        case 4: return launch_render_if_fits<N, 4>(h, p);
-        case 5: return launch_render_if_fits<N, 5>(h, p);
-        case 6: return launch_render_if_fits<N, 6>(h, p);
-        case 7: return launch_render_if_fits<N, 7>(h, p);
-    }
-    return fail(OHS_ERR_INVALID, "unsupported streams-per-CTA %d", h->G);
-}
-
-int launch_render(ohs_engine* h, const RenderParams& p) {
-    switch (h->N) {
-        case 128: return launch_render_n<128>(h, p);
-        case 256: return launch_render_n<256>(h, p);
-        case 512: return launch_render_n<512>(h, p);
-        case 1024: return launch_render_n<1024>(h, p);
-        case 2048: return launch_render_n<2048>(h, p);
-    }
-    return fail(OHS_ERR_INVALID, "unsupported block size %d", h->B);
-}
-
-template <int N> bool render_fits_n(int G) {
-    switch (G) {
-        case 1: return RenderSmem<N, 1>::kFits; case 2: return RenderSmem<N, 2>::kFits; case 3: return RenderSmem<N, 3>::kFits;
-        case 4: return RenderSmem<N, 4>::kFits; case 5: return RenderSmem<N, 5>::kFits; case 6: return RenderSmem<N, 6>::kFits;
-        case 7: return RenderSmem<N, 7>::kFits;
-    }
-    return false;
-}
-
 bool render_fits(int N, int G) {
     switch (N) {
-        case 128: return render_fits_n<128>(G); case 256: return render_fits_n<256>(G); case 512: return render_fits_n<512>(G);
-        case 1024: return render_fits_n<1024>(G); case 2048: return render_fits_n<2048>(G);
+        case 128: return render_fits_128(G); case 256: return render_fits_256(G); case 512: return render_fits_512(G);
+        case 1024: return render_fits_1024(G); case 2048: return render_fits_2048(G);
     }
     return false;
 }
+
+// per-device "attribute already set" flags of the small kernels; handles on different threads may race here, hence
+// atomic (setting an attribute twice is harmless)
+struct AttrOnce {
+    std::atomic<unsigned char> done[64];
+    bool need(int dev) const { return dev >= 0 && dev < 64 && !done[dev].load(std::memory_order_acquire); }
+    void mark(int dev) { done[dev].store(1, std::memory_order_release); }
+};
 
 template <int N> int launch_setup_n(ohs_engine* h, int max_parts, int n_sets) {
     using SM = SetupSmem<N>;
-    static bool attr_set[64] = {};
-    int dev = h->cfg.device;
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    static AttrOnce once;
+    const int dev = h->cfg.device;
+    if (once.need(dev)) {
         OHS_CUDA(cudaFuncSetAttribute(setup_filters_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kBytes));
-        attr_set[dev] = true;
+        once.mark(dev);
     }
     dim3 grid(max_parts, n_sets);
     setup_filters_kernel<N><<<grid, SM::T, SM::kBytes, h->stream>>>(h->d_ir, h->d_filt, h->d_tw, h->d_set_list, h->d_set_parts, h->pmax);
@@ -220,30 +202,34 @@ int commit_filters(ohs_engine* h) {
     int rc = upload_bindings(h);
     if (rc) return rc;
     if (!h->any_set_dirty) return OHS_OK;
+    // every dirty set's taps go into the host mirror, ONE copy uploads the span of dirty sets and ONE launch transforms
+    // them (config 4 binds a set per stream: thousands of sets per commit)
     const int n_sets = h->cfg.n_hrir_sets;
-    const size_t per_path = (size_t)h->pmax * h->B;
+    const size_t per_path = (size_t)h->pmax * h->B, per_set = 4 * per_path;
+    if (h->h_ir_padded.size() != per_set * n_sets) h->h_ir_padded.assign(per_set * n_sets, 0.f);
     std::vector<int> list;
-    std::vector<float> padded(4 * per_path);
-    int max_parts = 1;
+    int max_parts = 1, lo = n_sets, hi = -1;
     for (int s = 0; s < n_sets; ++s) {
         if (!h->set_dirty[s]) continue;
-        std::fill(padded.begin(), padded.end(), 0.f);
+        float* dst = h->h_ir_padded.data() + (size_t)s * per_set;
+        std::fill(dst, dst + per_set, 0.f);
         int parts = 1;
         for (int p = 0; p < 4; ++p) {
             const std::vector<float>& ir = h->h_ir[(size_t)s * 4 + p];
-            std::copy(ir.begin(), ir.end(), padded.begin() + p * per_path);
+            std::copy(ir.begin(), ir.end(), dst + p * per_path);
             parts = std::max(parts, h->h_path_parts[(size_t)s * 4 + p]);
         }
         h->h_set_parts[s] = parts;
         max_parts = std::max(max_parts, parts);
-        OHS_CUDA(cudaMemcpyAsync(h->d_ir + (size_t)s * 4 * per_path, padded.data(), sizeof(float) * padded.size(), cudaMemcpyHostToDevice, h->stream));
-        OHS_CUDA(cudaStreamSynchronize(h->stream));  // `padded` is reused
+        lo = std::min(lo, s); hi = std::max(hi, s);
         list.push_back(s);
     }
+    OHS_CUDA(cudaMemcpyAsync(h->d_ir + (size_t)lo * per_set, h->h_ir_padded.data() + (size_t)lo * per_set,
+                             sizeof(float) * per_set * (size_t)(hi - lo + 1), cudaMemcpyHostToDevice, h->stream));
     OHS_CUDA(cudaMemcpyAsync(h->d_set_parts, h->h_set_parts.data(), sizeof(int) * n_sets, cudaMemcpyHostToDevice, h->stream));
     OHS_CUDA(cudaMemcpyAsync(h->d_set_list, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, h->stream));
     OHS_CUDA(cudaMemcpyAsync(h->d_set_flags, h->set_dirty.data(), n_sets, cudaMemcpyHostToDevice, h->stream));
-    OHS_CUDA(cudaStreamSynchronize(h->stream));
+    OHS_CUDA(cudaStreamSynchronize(h->stream));  // pageable sources (`list` is a local) must be consumed before returning
     rc = launch_setup(h, max_parts, (int)list.size());
     if (rc) return rc;
     // set_ir clears the history of the streams that use the set (src/dsp/convolution.rs:135-138)
@@ -320,6 +306,29 @@ int check_audio_args(ohs_engine* h, const void* in, const void* out, size_t n_fr
     return OHS_OK;
 }
 
+// called once, from ohs_create (the only place the environment is consulted)
+// frames per staging chunk of the host-pointer path: whole blocks, about stage_bytes per buffer, at least one block
+size_t stage_chunk_frames(const ohs_engine* h, size_t n_frames) {
+    const size_t rows = (size_t)h->cfg.n_streams * 2;
+    size_t chunk = h->stage_bytes / (rows * sizeof(float));
+    chunk = std::max<size_t>(h->B, (chunk / h->B) * h->B);
+    return std::min(chunk, (n_frames + 3) / 4 * 4);
+}
+
+int ensure_stage_buffers(ohs_engine* h, size_t chunk) {
+    if (chunk <= h->stage_frames) return OHS_OK;
+    const size_t rows = (size_t)h->cfg.n_streams * 2;
+    OHS_CUDA(cudaStreamSynchronize(h->stream));
+    OHS_CUDA(cudaStreamSynchronize(h->d2h));
+    for (int i = 0; i < kPipe; ++i) {
+        if (h->d_stage[i]) OHS_CUDA(cudaFree(h->d_stage[i]));
+        h->d_stage[i] = nullptr;
+        OHS_CUDA(cudaMalloc(&h->d_stage[i], rows * chunk * sizeof(float)));
+    }
+    h->stage_frames = chunk;
+    return OHS_OK;
+}
+
 int pick_streams_per_cta(const ohs_engine* h) {
     if (const char* e = getenv("OHS_STREAMS_PER_CTA")) {
         const int g = atoi(e);
@@ -346,11 +355,11 @@ constexpr int kTimeBatch = 8;  // consecutive blocks a bin_conv_kernel thread ac
 
 template <int N> int launch_inverse(ohs_engine* h, float* d_out, int K, size_t row_stride) {
     constexpr size_t smem = sizeof(float2) * 2 * padded_len(N);
-    static bool attr_set[64] = {};
+    static AttrOnce once;
     const int dev = h->cfg.device;
-    if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !attr_set[dev]) {
+    if (smem > 48 * 1024 && once.need(dev)) {
         OHS_CUDA(cudaFuncSetAttribute(inverse_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[dev] = true;
+        once.mark(dev);
     }
     inverse_kernel<N><<<dim3(K, h->cfg.n_streams), fft_threads(N), smem, h->stream>>>(h->d_wlin, d_out, h->d_tw, h->d_stream_gain, K,
                                                                                       (long long)row_stride);
@@ -363,20 +372,37 @@ template <int N> int launch_inverse(ohs_engine* h, float* d_out, int K, size_t r
 // time-ordered buffer, (2) the render kernel in spectra-only mode (EQ, forward FFT, ring and buffer writes), (3) the
 // per-bin convolution along time, (4) the inverse transforms.  The delay-line ring, the overlap-save block and the EQ
 // state end up exactly where the block-by-block path leaves them, so the two can be mixed freely between calls.
-int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float* d_out, size_t row_stride) {
+// whether a call of n_blocks takes the time-batched route
+bool time_batch_eligible(const ohs_engine* h, int n_blocks) {
+    return h->time_batch && h->conv_enable && h->pmax >= 8 && n_blocks >= kTimeBatch && h->cfg.n_streams <= 65535;  // (grid.y = stream)
+}
+
+// Scratch of the time-batched route for calls of n_blocks (ohs_prepare calls this ahead of time so that no allocation
+// happens inside a timed call).  1: does not fit the 2 GiB budget (the caller stays on the block-by-block kernel).
+int ensure_time_batch_scratch(ohs_engine* h, int n_blocks) {
     const size_t S = (size_t)h->cfg.n_streams, N = (size_t)h->N, hist = (size_t)h->pmax - 1;
     const size_t budget = (size_t)2 << 30;
     const size_t per_block = 2 * S * N * sizeof(float2), fixed = S * hist * N * sizeof(float2);
     size_t kc = fixed < budget ? (budget - fixed) / per_block : 0;
-    kc = std::min<size_t>(std::min<size_t>(kc, 64), (size_t)p.n_blocks);
-    if (kc < (size_t)kTimeBatch) return 1;  // does not fit the scratch budget: caller falls back to the block-by-block kernel
+    kc = std::min<size_t>(std::min<size_t>(kc, 64), (size_t)n_blocks);
+    if (kc < (size_t)kTimeBatch) return 1;
     if (kc > h->zlin_blocks) {
+        OHS_CUDA(cudaStreamSynchronize(h->stream));
         if (h->d_zlin) OHS_CUDA(cudaFree(h->d_zlin));
         if (h->d_wlin) OHS_CUDA(cudaFree(h->d_wlin));
         h->d_zlin = h->d_wlin = nullptr; h->zlin_blocks = 0;
         OHS_CUDA(cudaMalloc(&h->d_zlin, S * (hist + kc) * N * sizeof(float2)));
         OHS_CUDA(cudaMalloc(&h->d_wlin, S * kc * N * sizeof(float2)));
         h->zlin_blocks = kc;
+    }
+    return OHS_OK;
+}
+
+int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float* d_out, size_t row_stride) {
+    const size_t S = (size_t)h->cfg.n_streams, N = (size_t)h->N, hist = (size_t)h->pmax - 1;
+    {
+        const int rc = ensure_time_batch_scratch(h, p.n_blocks);
+        if (rc) return rc;   // 1: caller falls back to the block-by-block kernel
     }
     const long long zstride = (long long)((hist + h->zlin_blocks) * N);
     const int total = p.n_blocks;
@@ -393,11 +419,11 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
         {
             const dim3 blk(128);
             const unsigned gx = (unsigned)((N / 2 + 31) / 32), gz = (unsigned)((S + 3) / 4);
-            static bool attr_set[64] = {};
+            static AttrOnce once;
             const int dev = h->cfg.device;
-            if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+            if (once.need(dev)) {
                 OHS_CUDA(cudaFuncSetAttribute(bin_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 16 * 128 * sizeof(float4))));
-                attr_set[dev] = true;
+                once.mark(dev);
             }
             // 16 blocks per thread (half the spectrum and filter traffic per FMA) from 16 blocks per sub-launch on:
             // measured faster than 8 at K = 16 (0.529 vs 0.560 ms), 32, 64 and 128 on config 5
@@ -461,6 +487,9 @@ int ohs_create(const ohs_config* cfg, ohs_engine** out) {
     h->N = 2 * B;
     h->pmax = (cfg->max_taps + B - 1) / B;
     h->G = pick_streams_per_cta(h);
+    if (const char* e = getenv("OHS_TIME_BATCH")) h->time_batch = atoi(e) != 0;
+    if (const char* e = getenv("OHS_STAGE_MB")) { const long mb = atol(e); if (mb >= 1 && mb <= 4096) h->stage_bytes = (size_t)mb << 20; }
+    if (const char* e = getenv("OHS_PDL")) h->dependent_launch = atoi(e) != 0;
     const int S = cfg->n_streams;
     const size_t per_path = (size_t)h->pmax * B;
 
@@ -671,10 +700,10 @@ int ohs_eq_reset(ohs_engine* h) {
     return OHS_OK;
 }
 
-int ohs_eq_frequency_response(ohs_engine* h, int eq_set, const float* freqs, float* out, size_t n) {
+int ohs_eq_frequency_response(ohs_engine* h, int eq_set, float sample_rate, const float* freqs, float* out, size_t n) {
     OHS_CHECK_HANDLE(h);
     if (eq_set < 0 || eq_set >= h->cfg.n_eq_sets || !freqs || !out) return fail(OHS_ERR_INVALID, "bad argument");
-    const float fs = h->cfg.sample_rate;
+    const float fs = sample_rate > 0.0f ? sample_rate : h->cfg.sample_rate;
     for (size_t i = 0; i < n; ++i) {
         float rr = 1.0f, ri = 0.0f;
         for (int b = 0; b < h->cfg.n_bands; ++b) {
@@ -715,6 +744,46 @@ int ohs_conv_reset(ohs_engine* h) {
     return clear_history(h, false);
 }
 
+int ohs_set_time_batch(ohs_engine* h, int enable) { OHS_CHECK_HANDLE(h); h->time_batch = enable ? 1 : 0; return OHS_OK; }
+
+int ohs_streams_per_cta(ohs_engine* h, int* out) {
+    OHS_CHECK_HANDLE(h);
+    if (!out) return fail(OHS_ERR_INVALID, "null output");
+    *out = h->G;
+    return OHS_OK;
+}
+
+int ohs_prepare(ohs_engine* h, size_t n_frames, int host_io) {
+    OHS_CHECK_HANDLE(h);
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc = commit_filters(h);
+    if (rc) return rc;
+    size_t per_launch = n_frames;
+    if (host_io) {
+        per_launch = stage_chunk_frames(h, n_frames);
+        rc = ensure_stage_buffers(h, per_launch);
+        if (rc) return rc;
+    }
+    const int n_blocks = (int)((per_launch + h->B - 1) / h->B);
+    if (time_batch_eligible(h, n_blocks)) {
+        rc = ensure_time_batch_scratch(h, n_blocks);
+        if (rc < 0) return rc;
+    }
+    OHS_CUDA(cudaStreamSynchronize(h->stream));
+    return OHS_OK;
+}
+
+int ohs_debug_trace(ohs_engine* h, unsigned long long* d_stamps) {
+    OHS_CHECK_HANDLE(h);
+#ifdef OHS_TRACE
+    h->d_trace = d_stamps;
+    return OHS_OK;
+#else
+    (void)d_stamps;
+    return fail(OHS_ERR_INVALID, "this library was built without -DOHS_TRACE");
+#endif
+}
+
 // ---- processing ---------------------------------------------------------------------------------------------
 int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_frames, size_t row_stride) {
     OHS_CHECK_HANDLE(h);
@@ -747,8 +816,7 @@ int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_
         p.filt_in_smem = h->h_set_parts[0];
     OHS_CUDA(cudaEventRecord(h->ev_k0, h->stream));
     // long responses over many blocks: convolve along time per bin instead of re-reading the delay line every block
-    bool batched = h->conv_enable && h->pmax >= 8 && p.n_blocks >= kTimeBatch && h->cfg.n_streams <= 65535;  // (grid.y = stream)
-    if (const char* e = getenv("OHS_TIME_BATCH")) batched = batched && atoi(e) != 0;
+    bool batched = time_batch_eligible(h, p.n_blocks);
     if (batched) {
         rc = process_time_batched(h, p, d_in, d_out, row_stride);
         if (rc < 0) return rc;
@@ -835,19 +903,10 @@ int ohs_process(ohs_engine* h, const float* in, float* out, size_t n_frames, siz
         return OHS_OK;
     }
     // chunk: whole blocks, about 24 MiB per staging buffer, at least one block
-    size_t target_bytes = (size_t)24 << 20;  // measured best on PCIe Gen5 x16 with both directions busy (tools/e2e_probe.py)
-    if (const char* e = getenv("OHS_STAGE_MB")) { const long mb = atol(e); if (mb >= 1 && mb <= 4096) target_bytes = (size_t)mb << 20; }
-    size_t chunk = target_bytes / (rows * sizeof(float));
-    chunk = std::max<size_t>(h->B, (chunk / h->B) * h->B);
-    chunk = std::min(chunk, (n_frames + 3) / 4 * 4);
-    if (chunk > h->stage_frames) {
-        for (int i = 0; i < kPipe; ++i) {
-            if (h->d_stage[i]) OHS_CUDA(cudaFree(h->d_stage[i]));
-            h->d_stage[i] = nullptr;
-            OHS_CUDA(cudaMalloc(&h->d_stage[i], rows * chunk * sizeof(float)));
-        }
-        h->stage_frames = chunk;
-    }
+    // 24 MiB by default: measured best on PCIe Gen5 x16 with both directions busy (tools/e2e_probe.py)
+    const size_t chunk = stage_chunk_frames(h, n_frames);
+    rc = ensure_stage_buffers(h, chunk);
+    if (rc) return rc;
     rc = commit_filters(h);
     if (rc) return rc;
     OHS_CUDA(cudaStreamSynchronize(h->stream));
@@ -931,18 +990,31 @@ int ohs_process_fifo(ohs_engine* h, const float* in, float* out, size_t n_frames
 }
 
 // ---- state export / import ----------------------------------------------------------------------------------
+// blob = StateHeader | delay line | overlap-save blocks | biquad states | FIFO residue (input rows, output rows)
+namespace {
+struct StateHeader {
+    uint32_t magic;      // 'OHSS'
+    int32_t abi, n_streams, n_bands, pmax, block, head, reserved;
+    uint64_t fifo_in_len, fifo_out_len, total_bytes;
+};
+constexpr uint32_t kStateMagic = 0x5353484Fu;
+size_t state_need(const ohs_engine* h, size_t fifo_in, size_t fifo_out) {
+    const size_t S = h->cfg.n_streams;
+    return sizeof(StateHeader) + sizeof(float2) * S * h->pmax * h->N + sizeof(float2) * S * h->B + sizeof(float4) * S * kMaxBands +
+           sizeof(float) * S * 2 * (fifo_in + fifo_out);
+}
+}  // namespace
+
 int ohs_state_bytes(ohs_engine* h, size_t* bytes) {
     OHS_CHECK_HANDLE(h);
     if (!bytes) return fail(OHS_ERR_INVALID, "null output");
-    const size_t S = h->cfg.n_streams;
-    *bytes = 16 + sizeof(float2) * S * h->pmax * h->N + sizeof(float2) * S * h->B + sizeof(float4) * S * kMaxBands;
+    *bytes = state_need(h, h->fifo_in_len, h->fifo_out_len);
     return OHS_OK;
 }
 
 int ohs_state_export(ohs_engine* h, void* host_buf, size_t bytes) {
     OHS_CHECK_HANDLE(h);
-    size_t need = 0;
-    ohs_state_bytes(h, &need);
+    const size_t need = state_need(h, h->fifo_in_len, h->fifo_out_len);
     if (!host_buf || bytes < need) return fail(OHS_ERR_INVALID, "state buffer too small (%zu < %zu)", bytes, need);
     OHS_CUDA(cudaSetDevice(h->cfg.device));
     int rc = commit_filters(h);
@@ -950,34 +1022,50 @@ int ohs_state_export(ohs_engine* h, void* host_buf, size_t bytes) {
     OHS_CUDA(cudaStreamSynchronize(h->stream));
     unsigned char* p = (unsigned char*)host_buf;
     const size_t S = h->cfg.n_streams;
-    int32_t hdr[4] = {OHS_ABI_VERSION, h->head, h->pmax, h->B};
-    memcpy(p, hdr, 16); p += 16;
+    StateHeader hdr{kStateMagic, OHS_ABI_VERSION, h->cfg.n_streams, kMaxBands, h->pmax, h->B, h->head, 0,
+                    (uint64_t)h->fifo_in_len, (uint64_t)h->fifo_out_len, (uint64_t)need};
+    memcpy(p, &hdr, sizeof(hdr)); p += sizeof(hdr);
     const size_t n0 = sizeof(float2) * S * h->pmax * h->N, n1 = sizeof(float2) * S * h->B, n2 = sizeof(float4) * S * kMaxBands;
     OHS_CUDA(cudaMemcpy(p, h->d_fdl, n0, cudaMemcpyDeviceToHost)); p += n0;
     OHS_CUDA(cudaMemcpy(p, h->d_prev, n1, cudaMemcpyDeviceToHost)); p += n1;
-    OHS_CUDA(cudaMemcpy(p, h->d_eqs, n2, cudaMemcpyDeviceToHost));
+    OHS_CUDA(cudaMemcpy(p, h->d_eqs, n2, cudaMemcpyDeviceToHost)); p += n2;
+    // what ohs_process_fifo has queued (src/dsp/convolution.rs:73-76 input_buffer / output_buffer), row by row
+    for (size_t r = 0; r < S * 2; ++r) { memcpy(p, h->fifo_in.data() + r * h->fifo_cap, h->fifo_in_len * sizeof(float)); p += h->fifo_in_len * sizeof(float); }
+    for (size_t r = 0; r < S * 2; ++r) { memcpy(p, h->fifo_out.data() + r * h->fifo_cap, h->fifo_out_len * sizeof(float)); p += h->fifo_out_len * sizeof(float); }
     return OHS_OK;
 }
 
 int ohs_state_import(ohs_engine* h, const void* host_buf, size_t bytes) {
     OHS_CHECK_HANDLE(h);
-    size_t need = 0;
-    ohs_state_bytes(h, &need);
-    if (!host_buf || bytes < need) return fail(OHS_ERR_INVALID, "state buffer too small (%zu < %zu)", bytes, need);
+    if (!host_buf || bytes < sizeof(StateHeader)) return fail(OHS_ERR_INVALID, "state blob too small for its header");
     const unsigned char* p = (const unsigned char*)host_buf;
-    int32_t hdr[4];
-    memcpy(hdr, p, 16); p += 16;
-    if (hdr[0] != OHS_ABI_VERSION || hdr[2] != h->pmax || hdr[3] != h->B) return fail(OHS_ERR_INVALID, "state blob does not match this engine's geometry");
+    StateHeader hdr;
+    memcpy(&hdr, p, sizeof(hdr)); p += sizeof(hdr);
+    if (hdr.magic != kStateMagic || hdr.abi != OHS_ABI_VERSION) return fail(OHS_ERR_INVALID, "not a state blob of ABI version %d", OHS_ABI_VERSION);
+    if (hdr.n_streams != h->cfg.n_streams || hdr.n_bands != kMaxBands || hdr.pmax != h->pmax || hdr.block != h->B)
+        return fail(OHS_ERR_INVALID, "state blob geometry (%d streams, %d partitions, block %d) does not match this engine (%d, %d, %d)",
+                    hdr.n_streams, hdr.pmax, hdr.block, h->cfg.n_streams, h->pmax, h->B);
+    if (hdr.head < 0 || hdr.head >= h->pmax) return fail(OHS_ERR_INVALID, "state blob ring head %d outside 0..%d", hdr.head, h->pmax - 1);
+    const size_t limit = (size_t)1 << 32;
+    if (hdr.fifo_in_len > limit || hdr.fifo_out_len > limit) return fail(OHS_ERR_INVALID, "state blob FIFO lengths are implausible");
+    const size_t need = state_need(h, (size_t)hdr.fifo_in_len, (size_t)hdr.fifo_out_len);
+    if (hdr.total_bytes != need || bytes != need) return fail(OHS_ERR_INVALID, "state blob is %zu bytes, header says %llu, geometry needs %zu", bytes, (unsigned long long)hdr.total_bytes, need);
     OHS_CUDA(cudaSetDevice(h->cfg.device));
     int rc = commit_filters(h);  // pending set_ir would otherwise clear the imported history later
     if (rc) return rc;
     OHS_CUDA(cudaStreamSynchronize(h->stream));
     const size_t S = h->cfg.n_streams;
     const size_t n0 = sizeof(float2) * S * h->pmax * h->N, n1 = sizeof(float2) * S * h->B, n2 = sizeof(float4) * S * kMaxBands;
-    h->head = hdr[1];
+    h->head = hdr.head;
     OHS_CUDA(cudaMemcpy(h->d_fdl, p, n0, cudaMemcpyHostToDevice)); p += n0;
     OHS_CUDA(cudaMemcpy(h->d_prev, p, n1, cudaMemcpyHostToDevice)); p += n1;
-    OHS_CUDA(cudaMemcpy(h->d_eqs, p, n2, cudaMemcpyHostToDevice));
+    OHS_CUDA(cudaMemcpy(h->d_eqs, p, n2, cudaMemcpyHostToDevice)); p += n2;
+    const size_t fi = (size_t)hdr.fifo_in_len, fo = (size_t)hdr.fifo_out_len;
+    const size_t cap = std::max(fi, fo) + (size_t)h->B;
+    h->fifo_in.assign(S * 2 * cap, 0.f); h->fifo_out.assign(S * 2 * cap, 0.f); h->fifo_cap = cap;
+    for (size_t r = 0; r < S * 2; ++r) { memcpy(h->fifo_in.data() + r * cap, p, fi * sizeof(float)); p += fi * sizeof(float); }
+    for (size_t r = 0; r < S * 2; ++r) { memcpy(h->fifo_out.data() + r * cap, p, fo * sizeof(float)); p += fo * sizeof(float); }
+    h->fifo_in_len = fi; h->fifo_out_len = fo;
     return OHS_OK;
 }
 

@@ -16,6 +16,7 @@ import numpy as np
 from . import _build
 
 OHS_ALL = -1
+ABI_VERSION = 2   # OHS_ABI_VERSION of include/ohs.h this binding was written against
 LSL, LSR, RSL, RSR = 0, 1, 2, 3
 PEAK, LOWSHELF, HIGHSHELF, LOWPASS, HIGHPASS, BANDPASS, NOTCH, ALLPASS = range(8)
 
@@ -51,12 +52,16 @@ SYMBOLS = [
     ("ohs_eq_set_band", C.c_int, [_VP, C.c_int, C.c_int, _f32p, C.c_int]),
     ("ohs_bind_stream_eq", C.c_int, [_VP, C.c_int, C.c_int]),
     ("ohs_eq_reset", C.c_int, [_VP]),
-    ("ohs_eq_frequency_response", C.c_int, [_VP, C.c_int, _f32p, _f32p, C.c_size_t]),
+    ("ohs_eq_frequency_response", C.c_int, [_VP, C.c_int, C.c_float, _f32p, _f32p, C.c_size_t]),
     ("ohs_set_eq_enable", C.c_int, [_VP, C.c_int]),
     ("ohs_set_conv_enable", C.c_int, [_VP, C.c_int]),
     ("ohs_set_bypass", C.c_int, [_VP, C.c_int]),
     ("ohs_set_gain", C.c_int, [_VP, C.c_int, C.c_float]),
     ("ohs_conv_reset", C.c_int, [_VP]),
+    ("ohs_set_time_batch", C.c_int, [_VP, C.c_int]),
+    ("ohs_streams_per_cta", C.c_int, [_VP, C.POINTER(C.c_int)]),
+    ("ohs_prepare", C.c_int, [_VP, C.c_size_t, C.c_int]),
+    ("ohs_debug_trace", C.c_int, [_VP, _VP]),
     ("ohs_process_device", C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_size_t]),
     ("ohs_process", C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_size_t]),
     ("ohs_process_fifo", C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_size_t]),
@@ -84,12 +89,20 @@ def load_library(build: bool = True):
     if build and _build.is_stale():
         try:
             _build.build_library()
-        except Exception:
+        except Exception as e:
             if not os.path.exists(path):
                 raise
+            import warnings
+
+            warnings.warn("libohs_cuda.so is older than its sources and could not be rebuilt (%s); loading the stale library" % e,
+                          RuntimeWarning, stacklevel=2)
     if not os.path.exists(path):
         raise OhsError(-3, "libohs_cuda.so is missing and could not be built; there is no CPU fallback")
     L = C.CDLL(path)
+    L.ohs_abi_version.restype = C.c_int
+    got = L.ohs_abi_version()
+    if got != ABI_VERSION:
+        raise OhsError(-1, "libohs_cuda.so has ABI version %d, this binding expects %d (rebuild the library)" % (got, ABI_VERSION))
     for name, res, args in SYMBOLS:
         fn = getattr(L, name)
         fn.restype = res
@@ -144,6 +157,7 @@ class Engine:
                  n_eq_sets: int = 1, device: int = 0, sample_rate: float = 48000.0):
         self._L = load_library()
         self.n_streams, self.block, self.max_taps, self.n_bands = n_streams, block, max_taps, n_bands
+        self.n_hrir_sets, self.n_eq_sets, self.device = n_hrir_sets, n_eq_sets, device
         self.sample_rate = sample_rate
         cfg = _Config(n_streams, block, max_taps, n_bands, n_hrir_sets, n_eq_sets, device, sample_rate)
         self._h = _VP()
@@ -206,10 +220,10 @@ class Engine:
     def eq_reset(self):
         _check(self._L.ohs_eq_reset(self._h))
 
-    def eq_frequency_response(self, freqs, eq_set: int = 0) -> np.ndarray:
+    def eq_frequency_response(self, freqs, eq_set: int = 0, sample_rate: float = 0.0) -> np.ndarray:
         f = _f32(freqs)
         out = np.zeros_like(f)
-        _check(self._L.ohs_eq_frequency_response(self._h, eq_set, f.ctypes.data_as(_f32p), out.ctypes.data_as(_f32p), f.size))
+        _check(self._L.ohs_eq_frequency_response(self._h, eq_set, sample_rate, f.ctypes.data_as(_f32p), out.ctypes.data_as(_f32p), f.size))
         return out
 
     # ---- switches
@@ -228,12 +242,33 @@ class Engine:
     def conv_reset(self):
         _check(self._L.ohs_conv_reset(self._h))
 
+    def set_time_batch(self, on: bool):
+        _check(self._L.ohs_set_time_batch(self._h, int(on)))
+
+    def streams_per_cta(self) -> int:
+        out = C.c_int()
+        _check(self._L.ohs_streams_per_cta(self._h, C.byref(out)))
+        return out.value
+
+    def prepare(self, n_frames: int, host_io: bool = False):
+        """Upload pending set-up and allocate scratch/staging for calls of n_frames, outside any timed region."""
+        _check(self._L.ohs_prepare(self._h, n_frames, int(host_io)))
+
+    def debug_trace(self, d_stamps: int):
+        _check(self._L.ohs_debug_trace(self._h, d_stamps))
+
     # ---- processing
     def process(self, x, out=None) -> np.ndarray:
         """Host flavour.  x[stream, channel, frame] float32; returns the rendered array (or fills `out`)."""
         x = _f32(x)
         assert x.ndim == 3 and x.shape[0] == self.n_streams and x.shape[1] == 2, x.shape
-        y = np.empty_like(x) if out is None else out
+        if out is None:
+            y = np.empty_like(x)
+        else:
+            y = out
+            if not (isinstance(y, np.ndarray) and y.dtype == np.float32 and y.shape == x.shape and y.flags["C_CONTIGUOUS"]
+                    and y.flags["WRITEABLE"]):
+                raise ValueError("out must be a writeable C-contiguous float32 array of shape %s" % (x.shape,))
         _check(self._L.ohs_process(self._h, x.ctypes.data, y.ctypes.data, x.shape[2], x.shape[2]))
         return y
 
@@ -339,4 +374,4 @@ class StereoParametricEQ:
         self._e.eq_reset()
 
     def calculate_frequency_response(self, sample_rate: float, frequencies):
-        return self._e.eq_frequency_response(frequencies)
+        return self._e.eq_frequency_response(frequencies, sample_rate=sample_rate)

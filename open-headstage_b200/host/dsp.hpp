@@ -119,9 +119,9 @@ class StereoParametricEQ {
         std::copy(io.begin() + n, io.end(), input_right.begin());
     }
     void reset_all_bands_state() { check(ohs_eq_reset(h_)); }
-    std::vector<float> calculate_frequency_response(float /*sample_rate*/, const std::vector<float>& frequencies) {
+    std::vector<float> calculate_frequency_response(float sample_rate, const std::vector<float>& frequencies) {
         std::vector<float> out(frequencies.size());
-        check(ohs_eq_frequency_response(h_, 0, frequencies.data(), out.data(), out.size()));
+        check(ohs_eq_frequency_response(h_, 0, sample_rate, frequencies.data(), out.data(), out.size()));
         return out;
     }
 

@@ -37,22 +37,44 @@ def broadcast_table(table: torch.Tensor, src: int = 0, group=None) -> torch.Tens
     return table
 
 
-def broadcast_filters(engine, src: int = 0, partitions: int | None = None, hrir_sets=(0,), group=None) -> None:
-    """Rank `src` must already have called set_ir for `hrir_sets`; the other ranks receive the spectra."""
+def set_partition_counts(engine, hrir_sets) -> list[int]:
+    """Partitions in use per HRIR set: the longest of its four paths (what the render kernel walks)."""
+    return [max(engine.num_partitions(p, s) for p in range(4)) for s in hrir_sets]
+
+
+def broadcast_filters(engine, src: int = 0, hrir_sets=None, group=None) -> None:
+    """Rank `src` must already have called set_ir for `hrir_sets` (default: every set of the engine); the other ranks
+    receive the whole device-resident spectra table and, per set, the partition count rank `src` derived from its
+    impulse responses."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    sets = list(range(engine.n_hrir_sets)) if hrir_sets is None else [int(s) for s in hrir_sets]
+    dev = torch.device("cuda", engine.device)
     if rank == src:
         engine.commit_filters()
         engine.sync()
+        counts = set_partition_counts(engine, sets)
+    else:
+        counts = [0] * len(sets)
     ptr, nbytes = engine.filter_table()
-    table = torch.as_tensor(DeviceMemory(ptr, nbytes), device="cuda")
-    torch.cuda.synchronize()
-    parts = torch.tensor([partitions or 0], dtype=torch.int32, device="cuda")
-    broadcast_table(table, src, group)
-    broadcast_table(parts, src, group)
-    torch.cuda.synchronize()
-    if rank != src:
-        for s in hrir_sets:
-            engine.mark_filters_external(s, int(parts.item()) or 1)
+    with torch.cuda.device(dev):
+        table = torch.as_tensor(DeviceMemory(ptr, nbytes), device=dev)
+        if table.data_ptr() != ptr:
+            raise RuntimeError("torch copied the engine's filter table instead of viewing it (device mismatch?)")
+        parts = torch.tensor(counts, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        broadcast_table(table, src, group)
+        broadcast_table(parts, src, group)
+        torch.cuda.synchronize(dev)
+    apply_received_partition_counts(engine, sets, parts.tolist(), rank == src)
+
+
+def apply_received_partition_counts(engine, hrir_sets, counts, is_src: bool) -> None:
+    """After a table broadcast: every receiving rank marks the sets as externally filled with the source's counts."""
+    for s, c in zip(hrir_sets, counts):
+        if c < 1:
+            raise RuntimeError("broadcast_filters: received partition count %d for HRIR set %d" % (c, s))
+        if not is_src:
+            engine.mark_filters_external(s, int(c))
 
 
 def reduce_bus(bus: torch.Tensor, dst: int = 0, group=None) -> torch.Tensor:

@@ -25,11 +25,13 @@ def _find_zlib_stream(buf: bytes, decoded_size: int) -> bytes:
     i = 0
     while True:
         i = buf.find(b"\x78", i)
-        if i < 0:
+        if i < 0 or i + 1 >= len(buf):
             raise ValueError("no zlib stream with decoded size %d" % decoded_size)
+        # a zlib header is two bytes whose big-endian value is a multiple of 31 (RFC 1950): 78 01 / 78 5E / 78 9C / 78 DA
         if buf[i + 1] in (0x01, 0x5E, 0x9C, 0xDA):
             try:
-                out = zlib.decompressobj().decompress(buf[i:])
+                # bounded: stop inflating as soon as the stream is longer than the dataset we are looking for
+                out = zlib.decompressobj().decompress(buf[i:], decoded_size + 1)
                 if len(out) == decoded_size:
                     return out
             except zlib.error:

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), "libohs_cuda.so does not export " + name
     bound = {s[0] for s in ohs.SYMBOLS}
     assert set(declared) == bound, set(declared) ^ bound
-    assert lib.ohs_abi_version() == 1
+    assert lib.ohs_abi_version() == ohs.engine.ABI_VERSION == 2
 
 
 def test_library_is_sm100a_native_code():

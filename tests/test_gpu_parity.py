@@ -501,7 +501,8 @@ def test_repeated_runs_are_bit_identical():
 @pytest.mark.parametrize("n_blocks", [1, 2, 3, 4, 5, 7])
 @pytest.mark.parametrize("mode", ["chain", "chain_disabled_band", "eq_only_ragged", "conv_only"])
 def test_short_launches_every_path(n_blocks, mode):
-    block, taps, n_streams = 256, 300, 9   # 9 streams: two CTAs at 7 streams per CTA would need >= 8; the last CTA is partial
+    block, taps, n_streams = 256, 300, 9   # 9 streams -> one stream per CTA (G = ceil(9 / #SM) = 1), nine full CTAs; partial
+    # last CTAs and G = 2..7 are covered by test_every_streams_per_cta_variant below
     n = block * n_blocks - (57 if mode == "eq_only_ragged" else 0)
     x = S.stream_inputs(n_streams, n, base_seed=900 + n_blocks)
     h = S.synthetic_hrir_set(taps, 50.0, seed=5)
@@ -564,11 +565,11 @@ def test_time_batched_long_response(block, taps, n_streams, n_blocks, monkeypatc
     # batched call, then block-by-block calls, then a batched call again on the same engine
     e = engine()
     cut1, cut2 = 16 * block, 16 * block + 2 * block
-    monkeypatch.setenv("OHS_TIME_BATCH", "1")
+    e.set_time_batch(True)
     parts = [e.process(x[:, :, :cut1])]
-    monkeypatch.setenv("OHS_TIME_BATCH", "0")
+    e.set_time_batch(False)
     parts.append(e.process(x[:, :, cut1:cut2]))
-    monkeypatch.setenv("OHS_TIME_BATCH", "1")
+    e.set_time_batch(True)
     if cut2 < n:
         parts.append(e.process(x[:, :, cut2:]))
     y_mixed = np.concatenate(parts, axis=2)
@@ -593,3 +594,195 @@ def test_time_batched_mixed_hrir_sets(monkeypatch):
         for s in range(n_streams):
             err = float(np.max(np.abs(y[s] - refs[s % 2][s])))
             assert err <= TOL, (mode, s, err)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# every render-kernel instantiation production can select: render_kernel<2*block, G>, G = 1..7 streams per CTA
+# (G = ceil(n_streams / #SM) up to 7, else 3 — csrc/ohs_api.cu pick_streams_per_cta), each with a partial last CTA,
+# a single-partition and a multi-partition response, the whole chain, two calls (state carried), K = 1 launches
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("g", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("block", [64, 128, 256, 512, 1024])
+def test_every_streams_per_cta_variant(block, g, monkeypatch):
+    monkeypatch.setenv("OHS_STREAMS_PER_CTA", str(g))
+    n_streams = 2 * g + 1 if g > 1 else 3          # g > 1: two full CTAs and a last CTA holding ONE stream
+    n_blocks = 6
+    x = S.stream_inputs(n_streams, block * n_blocks, base_seed=1500 + g)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL)
+    for taps in (block, 2 * block + block // 2):    # P = 1 (fused single-partition path at N = 512) and P = 3
+        h = S.synthetic_hrir_set(taps, taps / 5.0, seed=41)
+        e = ohs.Engine(n_streams, block, taps)
+        if e.streams_per_cta() != g:
+            assert g > 1   # G = 1 always fits
+            pytest.skip("render_kernel<%d,%d> does not fit in shared memory; production never selects it" % (2 * block, g))
+        e.set_hrir_set(h); e.eq_set_preset(S.EQ_PRESET_TYPICAL); e.set_eq_enable(True); e.set_gain(0.5)
+        ref = oracle_render(x, block, h, coeffs, [1] * 10, 0.5)
+        y = np.concatenate([e.process(x[:, :, :4 * block]), e.process(x[:, :, 4 * block:5 * block]), e.process(x[:, :, 5 * block:])], axis=2)
+        err = float(np.max(np.abs(y - ref)))
+        assert err <= TOL, (taps, err)
+        # EQ stage alone through the same instantiation: bit-exact
+        q = ohs.Engine(n_streams, block, 1)
+        assert q.streams_per_cta() == g
+        q.set_conv_enable(False); q.set_eq_enable(True)
+        for b in range(10):
+            q.eq_set_band(b, coeffs[b], True)
+        yq = q.process(x)
+        s = n_streams - 1                            # the lone stream of the partial CTA
+        o = O.StereoParametricEQ(10, FS)
+        for b in range(10):
+            o.set_band_raw(b, coeffs[b], True)
+        l, r = o.process_block(x[s, 0], x[s, 1])
+        assert yq[s, 0].tobytes() == l.tobytes() and yq[s, 1].tobytes() == r.tobytes()
+
+
+@pytest.mark.parametrize("cfg,n_streams,expect_g,n_blocks", [(3, 1210, 3, 24), (2, 1024, 7, 16), (2, 600, 5, 16), (3, 300, 3, 24)])
+def test_production_instantiations_at_width(cfg, n_streams, expect_g, n_blocks):
+    """The instantiation the host picks BY ITSELF at production widths: config 3 (block 128, 512 taps, P = 4) beyond
+    7 streams per SM -> render_kernel<256,3>, dense role packing, several CTAs per SM, partial last CTA (1210 = 403*3+1);
+    config 2 (1024 streams -> <512,7>, 600 -> <512,5>).  Sampled streams against the oracle, every stream against its
+    tiled twin."""
+    c = S.CONFIGS[cfg]
+    block, taps = c["block"], c["taps"]
+    h = S.synthetic_hrir_set(taps, c["decay"])
+    n = block * n_blocks
+    unique = 10
+    x = S.stream_inputs(n_streams, n, unique=unique)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL)
+    e = ohs.Engine(n_streams, block, taps)
+    assert e.streams_per_cta() == expect_g, e.streams_per_cta()
+    e.set_hrir_set(h); e.eq_set_preset(S.EQ_PRESET_TYPICAL); e.set_eq_enable(True); e.set_gain(0.5)
+    y = np.concatenate([e.process(x[:, :, :n // 2]), e.process(x[:, :, n // 2:])], axis=2)
+    ref = oracle_render(x[:unique], block, h, coeffs, [1] * 10, 0.5)
+    assert float(np.max(np.abs(y[:unique] - ref))) <= TOL
+    # tiled inputs -> tiled outputs, bit for bit, wherever the stream sits (CTA, slot in the CTA, SM)
+    for s in range(unique, n_streams):
+        assert y[s].tobytes() == y[s % unique].tobytes(), s
+
+
+# ------------------------------------------------------------------------------------------------------------
+# small rows: magnitude response helper, SOFA wiring and AutoEQ ingestion driven into the real engine, the
+# multi-partition table hand-over of the broadcast path, state-blob validation
+# ------------------------------------------------------------------------------------------------------------
+def test_eq_frequency_response_product_function():
+    """ohs_eq_frequency_response (src/dsp/parametric_eq.rs:191-209) against the oracle's restatement and against an
+    independent f64 evaluation (scipy freqz) of the same coefficients; disabled bands are skipped; sample_rate honoured."""
+    freqs = np.geomspace(20.0, 20000.0, 64).astype(np.float32)
+    for fs in (48000.0, 44100.0):
+        e = ohs.Engine(1, 256, 1, sample_rate=fs)
+        o = O.StereoParametricEQ(10, fs)
+        coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL, fs)
+        for b in range(10):
+            e.eq_set_band(b, coeffs[b], b != 6)
+            o.set_band_raw(b, coeffs[b], b != 6)
+        got = e.eq_frequency_response(freqs, sample_rate=fs)
+        want = o.calculate_frequency_response(fs, freqs)
+        assert np.max(np.abs(got / want - 1.0)) <= 1e-6
+        truth = np.ones(freqs.size)
+        for b in range(10):
+            if b == 6:
+                continue
+            c = coeffs[b].astype(np.float64)
+            _, hh = sps.freqz([c[0], c[1], c[2]], [1.0, c[3], c[4]], worN=freqs.astype(np.float64), fs=fs)
+            truth *= np.abs(hh)
+        assert np.max(np.abs(got / truth - 1.0)) <= 2e-4
+        # the mirror object passes its sample_rate argument through (reference signature)
+        m = ohs.StereoParametricEQ(10, 48000.0)
+        for b in range(10):
+            m.update_band_coeffs(b, fs, ohs.BandConfig(*S.EQ_PRESET_TYPICAL[b], b != 6))
+        assert np.max(np.abs(m.calculate_frequency_response(fs, freqs) / want - 1.0)) <= 1e-6
+    assert e.eq_frequency_response(freqs, sample_rate=0.0).tobytes() == e.eq_frequency_response(freqs, sample_rate=44100.0).tobytes()
+
+
+def test_sofa_wiring_and_autoeq_into_the_real_engine(cipic):
+    """SURVEY 8f rows 1 and 4 end to end: SOFA directions -> four set_ir calls, AutoEQ CSV -> update_band_coeffs, on the
+    GPU engine, against the oracle given the same indices and the same parsed bands."""
+    from open_headstage_b200 import autoeq, sofa
+
+    hr = sofa.from_arrays(cipic["ir"], cipic["pos"], float(cipic["fs"]))
+    e = ohs.Engine(2, 512, 200, sample_rate=FS)
+    il, ir_ = sofa.wire_speakers(e, hr, sofa.ui_azimuth_to_sofa(-30.0), 0.0, sofa.ui_azimuth_to_sofa(30.0), 0.0)
+    assert (il, ir_) == (308, 908)
+    csv_text = "Filter-Type,Fc,Q,Gain\n" + "\n".join(
+        "%s,%g,%g,%g" % ({S.LOWSHELF: "LS", S.PEAK: "PK", S.HIGHSHELF: "HS"}[t], fc, q, g) for (t, fc, q, g) in S.EQ_PRESET_TYPICAL) + "\n"
+    bands = autoeq.parse_autoeq_csv(csv_text)
+    assert len(bands) == 10
+    autoeq.apply_to_engine(e, bands)
+    e.set_eq_enable(True); e.set_gain(0.5)
+    x = S.stream_inputs(2, 512 * 12, base_seed=1700)
+    y = e.process(x)
+    ir = cipic["ir"]
+    irs = [ir[308, 0], ir[308, 1], ir[908, 0], ir[908, 1]]
+    coeffs = np.stack([O.eq_design(b.filter_type, FS, b.frequency, b.q, b.gain) for b in bands])
+    ref = oracle_render(x, 512, irs, coeffs, [1] * 10, 0.5)
+    assert float(np.max(np.abs(y - ref))) <= TOL
+    assert np.abs(y).max() > 0.05
+
+
+def test_filter_table_handover_multi_partition():
+    """What a broadcast receiver does (parallel.broadcast_filters): engine B never sees the impulse responses, it gets
+    engine A's device-resident spectra table plus A's per-set partition counts — for a response LONGER than one block
+    (the count used to be lost)."""
+    import torch
+    from open_headstage_b200 import parallel as P
+
+    block, taps = 256, 900   # 4 partitions
+    h = S.synthetic_hrir_set(taps, 150.0, seed=3)
+    x = S.stream_inputs(3, block * 8, base_seed=1800)
+    a = ohs.Engine(3, block, taps, n_bands=0); a.set_hrir_set(h); a.commit_filters(); a.sync()
+    b = ohs.Engine(3, block, taps, n_bands=0)
+    counts = P.set_partition_counts(a, [0])
+    assert counts == [4]
+    pa, na = a.filter_table(); pb, nb = b.filter_table()
+    assert na == nb
+    ta = torch.as_tensor(P.DeviceMemory(pa, na), device="cuda:0"); tb = torch.as_tensor(P.DeviceMemory(pb, nb), device="cuda:0")
+    assert ta.data_ptr() == pa and tb.data_ptr() == pb
+    tb.copy_(ta); torch.cuda.synchronize()
+    P.apply_received_partition_counts(b, [0], counts, is_src=False)
+    assert b.num_partitions(0) == 4
+    assert b.process(x).tobytes() == a.process(x).tobytes()
+    with pytest.raises(RuntimeError):
+        P.apply_received_partition_counts(b, [0], [0], is_src=False)
+    # world size 1: the public call is a no-op broadcast that still validates the counts
+    P.broadcast_filters(a)
+
+
+def test_state_blob_validation_and_fifo_residue():
+    import struct
+
+    h = S.synthetic_hrir_set(600, 100.0, seed=4)
+    x = S.stream_inputs(2, 1000, base_seed=1900)
+
+    def make(n_streams=2, taps=600):
+        e = ohs.Engine(n_streams, 256, taps)
+        e.set_hrir_set(h[:, :taps]); e.eq_set_preset(S.EQ_PRESET_TYPICAL); e.set_eq_enable(True); e.set_gain(0.5)
+        return e
+
+    # FIFO residue travels with the blob: ragged host blocks, export in the middle, resume on a fresh engine
+    a = make()
+    whole = np.concatenate([a.process_fifo(x[:, :, i:i + 100]) for i in range(0, 1000, 100)], axis=2)
+    b = make()
+    first = np.concatenate([b.process_fifo(x[:, :, i:i + 100]) for i in range(0, 400, 100)], axis=2)
+    blob = b.state_export()
+    c = make()
+    c.state_import(blob)
+    second = np.concatenate([c.process_fifo(x[:, :, i:i + 100]) for i in range(400, 1000, 100)], axis=2)
+    assert np.concatenate([first, second], axis=2).tobytes() == whole.tobytes()
+    # a corrupt ring head, a truncated blob, a padded blob and a blob from another geometry are all rejected
+    magic, abi, n_streams, n_bands, pmax, block, head, _ = struct.unpack_from("<I7i", blob, 0)
+    assert (n_streams, pmax, block) == (2, 3, 256) and 0 <= head < pmax
+    for bad_head in (-1, pmax, 1 << 20):
+        bad = bytearray(blob); struct.pack_into("<i", bad, 24, bad_head)
+        with pytest.raises(ohs.OhsError):
+            c.state_import(bytes(bad))
+    with pytest.raises(ohs.OhsError):
+        c.state_import(blob[:-4])
+    with pytest.raises(ohs.OhsError):
+        c.state_import(blob + b"\0\0\0\0")
+    with pytest.raises(ohs.OhsError):
+        make(n_streams=3).state_import(blob)
+    with pytest.raises(ohs.OhsError):
+        make(taps=256).state_import(blob)
+    with pytest.raises(ohs.OhsError):
+        c.state_import(b"\0" * len(blob))
+    with pytest.raises(ValueError):
+        c.process(np.zeros((2, 2, 256), np.float32), out=np.zeros((2, 2, 256), np.float64))
