@@ -163,7 +163,10 @@ int ohs_sync(ohs_engine* h);
 int ohs_cuda_stream(ohs_engine* h, void** stream);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches evidence). */
 int ohs_launch_count(ohs_engine* h, uint64_t* out);
-/* Elapsed device time (ms) of the render kernels of the most recent ohs_process_device call; blocks until done. */
+/* Elapsed device time (ms) of the kernels of the most recent ohs_process_device call made while timing was enabled;
+ * blocks until they are done.  Timing is off by default: it brackets every call with two CUDA events, which keeps
+ * back-to-back per-block calls from overlapping their launch with the previous call's tail. */
+int ohs_enable_timing(ohs_engine* h, int enable);
 int ohs_last_kernel_ms(ohs_engine* h, float* ms);
 
 /* Object mixdown (BASELINE config 4; an extension — the reference has no multi-source mode): sums the rendered

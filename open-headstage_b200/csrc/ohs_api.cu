@@ -55,7 +55,7 @@ struct ohs_engine {
     int B = 0, N = 0, pmax = 1, G = 1;
     cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
-    bool timed = false;
+    bool timing = false, timed = false;   // ohs_enable_timing: event pair around the kernels of a process call
 
     // device
     int* d_stream_hrir = nullptr;
@@ -87,6 +87,7 @@ struct ohs_engine {
     int time_batch = 1;            // OHS_TIME_BATCH / ohs_set_time_batch: 0 keeps long responses on the block-by-block kernel
     size_t stage_bytes = (size_t)24 << 20;  // OHS_STAGE_MB: staging chunk of the host-pointer path
     bool dependent_launch = true;  // OHS_PDL=0 switches programmatic dependent launches off
+    int latency_blocks = 2;        // OHS_LATENCY_BLOCKS: launches of up to this many blocks run the latency variant
     unsigned long long* d_trace = nullptr;  // ohs_debug_trace (OHS_TRACE builds)
     std::vector<float> h_ir_padded;         // [set][4][pmax*B] host mirror of d_ir, uploaded in one copy per commit
 
@@ -110,7 +111,9 @@ namespace {
 using namespace ohs;
 
 int launch_render(ohs_engine* h, const RenderParams& p, int first_stream = 0) {
-    RenderLaunch L{h->G, h->cfg.device, h->stream, first_stream, h->dependent_launch};
+    // few blocks per launch: nothing overlaps inside the launch, so the variant built for latency runs it
+    const bool latency = p.n_blocks <= h->latency_blocks && !p.spectra_only;
+    RenderLaunch L{h->G, h->cfg.device, h->stream, first_stream, latency, h->dependent_launch};
     RenderParams q = p;
     q.trace = h->d_trace;
     cudaError_t e = cudaErrorInvalidValue;
@@ -490,6 +493,7 @@ int ohs_create(const ohs_config* cfg, ohs_engine** out) {
     if (const char* e = getenv("OHS_TIME_BATCH")) h->time_batch = atoi(e) != 0;
     if (const char* e = getenv("OHS_STAGE_MB")) { const long mb = atol(e); if (mb >= 1 && mb <= 4096) h->stage_bytes = (size_t)mb << 20; }
     if (const char* e = getenv("OHS_PDL")) h->dependent_launch = atoi(e) != 0;
+    if (const char* e = getenv("OHS_LATENCY_BLOCKS")) h->latency_blocks = atoi(e);
     const int S = cfg->n_streams;
     const size_t per_path = (size_t)h->pmax * B;
 
@@ -814,7 +818,8 @@ int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_
     p.filt_in_smem = 0;
     if (h->cfg.n_hrir_sets == 1 && h->N <= 512 && (size_t)h->h_set_parts[0] * h->N * sizeof(float4) <= 16 * 1024)
         p.filt_in_smem = h->h_set_parts[0];
-    OHS_CUDA(cudaEventRecord(h->ev_k0, h->stream));
+    // (off by default: an event between two launches keeps the second from starting while the first drains)
+    if (h->timing) OHS_CUDA(cudaEventRecord(h->ev_k0, h->stream));
     // long responses over many blocks: convolve along time per bin instead of re-reading the delay line every block
     bool batched = time_batch_eligible(h, p.n_blocks);
     if (batched) {
@@ -827,8 +832,7 @@ int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_
         if (rc) return rc;
         if (h->conv_enable) h->head = (int)(((size_t)h->head + p.n_blocks) % (size_t)h->pmax);
     }
-    OHS_CUDA(cudaEventRecord(h->ev_k1, h->stream));
-    h->timed = true;
+    if (h->timing) { OHS_CUDA(cudaEventRecord(h->ev_k1, h->stream)); h->timed = true; }
     return OHS_OK;
 }
 
@@ -853,10 +857,12 @@ int ohs_launch_count(ohs_engine* h, uint64_t* out) {
     return OHS_OK;
 }
 
+int ohs_enable_timing(ohs_engine* h, int enable) { OHS_CHECK_HANDLE(h); h->timing = enable != 0; if (!enable) h->timed = false; return OHS_OK; }
+
 int ohs_last_kernel_ms(ohs_engine* h, float* ms) {
     OHS_CHECK_HANDLE(h);
     if (!ms) return fail(OHS_ERR_INVALID, "null output");
-    if (!h->timed) return fail(OHS_ERR_INVALID, "no kernel has been launched yet");
+    if (!h->timed) return fail(OHS_ERR_INVALID, "no timed process call yet (ohs_enable_timing first)");
     OHS_CUDA(cudaEventSynchronize(h->ev_k1));
     OHS_CUDA(cudaEventElapsedTime(ms, h->ev_k0, h->ev_k1));
     return OHS_OK;

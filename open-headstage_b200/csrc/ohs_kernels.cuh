@@ -66,7 +66,7 @@ struct RenderParams {
     const float4* filt;         // [set][pmax][even bins | odd bins] {A.re, A.im, C.re, C.im}, 1/N folded in
     const int* set_parts;       // [set] partitions in use
     float2* fdl;                // [stream][pmax][N] packed spectra ring (unused when every set has 1 partition)
-    float2* prev;               // [stream][B] last filtered input block (overlap-save history)
+    float2* prev;               // [stream][2][B] f32 planar (left row, right row): last filtered input block (overlap-save history)
     const float* eqc;           // [eq_set][kMaxBands][kEqCoefStride]
     float4* eqs;                // [stream][kMaxBands] {s1L, s1R, s2L, s2R}
     const float2* tw;           // [N] exp(-2*pi*i*m/N)
@@ -98,7 +98,12 @@ struct RenderParams {
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+// complex product with the contraction pinned (one rounded product, one FMA per component): every instantiation of
+// the transforms — throughput and latency variant, fused and general single-partition path — rounds identically, so
+// a stream's output does not depend on how many blocks a call renders
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+    return make_float2(fmaf(a.x, w.x, -__fmul_rn(a.y, w.y)), fmaf(a.x, w.y, __fmul_rn(a.y, w.x)));
+}
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 
 // shared-memory index padding of the complex ping-pong buffers: 16 bytes after every 16 float2.  Adjacent pairs stay
@@ -337,15 +342,27 @@ template <int N> inline void fill_twiddles(float2* out) {
 // ---------------------------------------------------------------------------------------------------------------
 // shared-memory carve-up of the render kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int N, int G> struct RenderSmem {
+// V = 0: the throughput variant (launches of many blocks: EQ of block t+1 overlaps the convolution of block t, so the
+// roles are sized for issue-slot balance).  V = 1, N = 512: the latency variant for launches of one or two blocks (the
+// reference's calling pattern, one call per host buffer), where nothing overlaps and a block's time is the EQ chain's
+// latency plus the transform's: twice the threads per stream in the transforms (6.0 k instead of 9.7 k cycles for a
+// lone block of config 2).  One band per lane in its EQ warps was measured too and is not faster there: five EQ
+// warps put two on one scheduler partition (36 cycles per step against 34).
+template <int N, int G, int V = 0> struct RenderSmem {
+    static_assert(V == 0 || (V == 1 && N == 512), "the latency variant exists for N = 512");
     static constexpr int B = N / 2;
-    static constexpr int T = fft_threads(N);                 // convolution threads per stream (one warp at N <= 512)
+    // convolution threads per stream (V = 0: one warp at N <= 512).  The latency variant doubles them where that keeps
+    // the radix plan (N = 512: 8 points per thread, radices 8-8-8 either way), so both variants round identically.
+    static constexpr int T = (V == 1 && N == 512) ? 2 * fft_threads(N) : fft_threads(N);
     static constexpr int NP = padded_len(N);
     // Bands per lane of the EQ warps.  2: five lanes per chain, six chains per warp (config 2: the issue slots of three
     // warps are what the CTA can spare).  1: ten lanes per chain, three chains per warp, half the instructions and a
     // single 12-cycle dependent chain per step — for the long blocks of N >= 1024, where a CTA holds few streams and
     // the 1024-step sequential chain per block is the floor of the launch (config 5).
     static constexpr int kEqBpl = (N >= 1024) ? 1 : 2;
+    // lane skew of the systolic chain in steps (= steps per unrolled iteration).  One band per lane runs a step in half
+    // the time, too fast for a 3-step shuffle flight: skew 8
+    static constexpr int kEqSkewSteps = (B >= 128) ? (kEqBpl == 1 ? 8 : kEqSkew) : 4;
     static constexpr int kEqCpw = 32 / (kMaxBands / kEqBpl);   // chains per EQ warp: 6 or 3
     static constexpr int kEqWarps = (2 * G + kEqCpw - 1) / kEqCpw;
     static constexpr int kEqThreads = 32 * kEqWarps;
@@ -369,7 +386,7 @@ template <int N, int G> struct RenderSmem {
     // Balancing pads the CTA with idle warp slots, which only pays when one CTA owns the SM (N >= 512: config 2 and the
     // long-BRIR config); smaller transforms run several CTAs per SM, which balances the partitions by itself, and
     // there the roles are packed densely.
-    static constexpr bool kBalanced = (N >= 512);
+    static constexpr bool kBalanced = (N >= 512) && V == 0;
     static constexpr int kEqWeight = OHS_EQ_WEIGHT;   // an EQ warp's load in units of a convolution warp's
     static constexpr Placement place() {
         Placement pl{};
@@ -417,7 +434,7 @@ template <int N, int G> struct RenderSmem {
     // filter spectra of a shared single-set, few-partition HRIR (configs 1-3) are staged here once per launch
     static constexpr size_t kFiltSmemBytes = (N <= 512) ? 16 * 1024 : 0;
     static constexpr size_t kFiltOff = kStageOff + sizeof(float) * kStageBufs * G * kStageStride;
-    static constexpr size_t kMbarOff = kFiltOff + kFiltSmemBytes;  // uint64_t stage_full[3], filt_full[2]
+    static constexpr size_t kMbarOff = kFiltOff + kFiltSmemBytes;  // uint64_t stage_full[3], filt_full[2], prologue_full
     static constexpr size_t kBytes = kMbarOff + 48;
     static constexpr bool kFits = kBytes <= 227 * 1024 && kThreads <= 1024;
     // Register budget.  Warps are allocated in groups of four; as many CTAs per SM as shared memory allows (up to
@@ -457,16 +474,16 @@ __device__ __forceinline__ float df2t_step(float x, float& s1, float& s2, float 
 // of a lane are two independent dependent-chains that cover each other's 4-cycle FP32 latency.  Every band's
 // recurrence is the strictly sequential reference recurrence (see df2t_step): bit-exact.
 template <bool V> struct Flag { static constexpr bool value = V; };
-template <int N, int G>
+template <int N, int G, int V>
 __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned char* smem, int stream0, int w) {
-    using SM = RenderSmem<N, G>;
+    using SM = RenderSmem<N, G, V>;
     constexpr int B = SM::B;
     constexpr int BPL = SM::kEqBpl;                    // bands per lane
     constexpr int LPC = kMaxBands / BPL;               // lanes per chain
     constexpr int CPW = SM::kEqCpw;                    // chains per warp
     // lane skew in steps = steps per unrolled iteration.  One band per lane runs a step in half the time, too fast for
     // a 3-step shuffle flight: skew 8.
-    constexpr int DL = (B >= 128) ? (BPL == 1 ? 8 : kEqSkew) : 4;
+    constexpr int DL = SM::kEqSkewSteps;
     constexpr int NQ = DL / 4;                         // float4 input loads per iteration
     constexpr int LL = DL - 1 + (BPL - 1);             // steps a lane runs behind its left neighbour: a shuffled value is used
                                                        // DL-1 steps after it was sent, band B one step after band A
@@ -497,18 +514,25 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     bool en_a = false, en_b = false;
     const int band_a = BPL * l, band_b = BPL * l + 1;
     const bool has_a = lane_valid && do_eq && band_a < p.n_bands, has_b = BPL == 2 && lane_valid && do_eq && band_b < p.n_bands;
+    // coefficients (constant across this handle's launches) before the wait for the previous launch, states after it
     if (has_a) {
         const float* cf = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + band_a) * kEqCoefStride;
         ab0 = cf[0]; ab1 = cf[1]; ab2 = cf[2]; aa1 = cf[3]; aa2 = cf[4]; en_a = cf[5] != 0.f;
-        const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + band_a);
-        as1 = st[ch]; as2 = st[2 + ch];
     }
     if (has_b) {
         const float* cf = p.eqc + ((size_t)p.stream_eq[s] * kMaxBands + band_b) * kEqCoefStride;
         bb0 = cf[0]; bb1 = cf[1]; bb2 = cf[2]; ba1 = cf[3]; ba2 = cf[4]; en_b = cf[5] != 0.f;
+    }
+    grid_dependency_wait();
+    if (has_a) {
+        const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + band_a);
+        as1 = st[ch]; as2 = st[2 + ch];
+    }
+    if (has_b) {
         const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + band_b);
         bs1 = st[ch]; bs2 = st[2 + ch];
     }
+    __syncthreads();   // the CTA's one common barrier: the staging warp has initialised the mbarriers
 
     OHS_STAMP_IF(threadIdx.x == 0, p, 2);
     // Input rows: block t sits in stage buffer t % 3 once that buffer's mbarrier has completed its (t/3)-th phase.
@@ -756,28 +780,70 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
 // every EQ thread has arrived at block t-3's FULL barrier (it read the rows before it arrived); the warp listens in on
 // that barrier and otherwise sleeps, so neither the EQ warps nor the convolution warps carry copy instructions.  A
 // ragged last block is loaded by the EQ warps themselves (eq_warp_main::wait_stage).
-template <int N, int G>
+template <int N, int G, int V>
 __device__ __forceinline__ void stager_warp_main(const RenderParams& p, unsigned char* smem, int stream0) {
-    using SM = RenderSmem<N, G>;
+    using SM = RenderSmem<N, G, V>;
     constexpr int B = SM::B;
     const int n_str = (p.n_streams - stream0) < G ? (p.n_streams - stream0) : G;
     const int row = threadIdx.x & 31;   // 2G <= 14 rows
-    auto issue = [&](int t) {
+    auto issue = [&](int t, bool reused) {
         if (t >= p.n_blocks || (t == p.n_blocks - 1 && p.tail_frames != B)) return;
         uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff) + (t % 3);
         float* dst_base = reinterpret_cast<float*>(smem + SM::kStageOff) + (size_t)(t % 3) * G * SM::kStageStride;
-        fence_proxy_async();            // the async-proxy writes stay behind the generic-proxy reads ordered by the barrier
+        if (reused) fence_proxy_async();   // the async-proxy writes stay behind the generic-proxy reads ordered by the barrier
         if (row == 0) mbar_expect_tx(full, (unsigned)(n_str * 2 * B * sizeof(float)));
         if (row < 2 * n_str) {
             const float* src = p.in + ((size_t)(stream0 - p.io_first_stream + (row >> 1)) * 2 + (row & 1)) * p.row_stride + (size_t)t * B;
             tma_load_1d(dst_base + (row >> 1) * SM::kStageStride + (row & 1) * SM::kRowR, src, (unsigned)(B * sizeof(float)), full);
         }
     };
-    issue(0); issue(1); issue(2);
+    // The CTA's prologue data also arrives by TMA, all of it in flight at once and none of it through registers: the
+    // twiddle tables and the shared filter spectra (constant across this handle's launches: issued BEFORE the wait for
+    // the previous launch), then block 0's input rows (the EQ warps start the moment they land), the overlap-save
+    // history rows of the CTA's streams into ring slot 2, and the next two blocks' rows.  Only the convolution warps wait
+    // for the prologue barrier.  Nothing has touched these buffers through the generic proxy yet: no proxy fence.
+    {
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
+        if (row == 0) {
+            mbar_init(&bars[0], 1);   // stage_full[0..2]: input rows of block t in stage buffer t % 3
+            mbar_init(&bars[1], 1);
+            mbar_init(&bars[2], 1);
+            mbar_init(&bars[3], 1);   // filt_full[0..1]: filter tiles of the long-impulse-response path
+            mbar_init(&bars[4], 1);
+            mbar_init(&bars[5], 1);   // prologue_full: twiddles, shared filter spectra, overlap-save history
+            fence_mbar_init();
+        }
+        __syncwarp();
+        OHS_STAMP_IF(row == 0, p, 10);
+        uint64_t* pro = bars + 5;
+        const unsigned tw_bytes = (unsigned)(sizeof(float2) * N);
+        const unsigned filt_bytes = (unsigned)(p.filt_in_smem * N * sizeof(float4));
+        const unsigned hist_bytes = p.conv_enable ? (unsigned)(n_str * 2 * B * sizeof(float)) : 0u;
+        if (row == 0) {
+            mbar_expect_tx(pro, tw_bytes + filt_bytes + hist_bytes);
+            tma_load_1d(smem + SM::kTwOff, p.tw, tw_bytes, pro);
+            // the fused single-partition path reads bin k at position k: its table lands in stream 0's (idle) FFT buffers
+            // and the convolution warps permute it into place; every other path keeps the global even-bins-first layout
+            if (filt_bytes) tma_load_1d(smem + (SM::kFusedMac && p.filt_in_smem == 1 ? SM::kZOff : SM::kFiltOff), p.filt, filt_bytes, pro);
+        }
+        OHS_STAMP_IF(row == 0, p, 11);
+        grid_dependency_wait();
+        OHS_STAMP_IF(row == 0, p, 12);
+        issue(0, false);
+        OHS_STAMP_IF(row == 0, p, 13);
+        if (hist_bytes && row < 2 * n_str) {
+            float* ring = reinterpret_cast<float*>(smem + SM::kRingOff);
+            tma_load_1d(ring + (row >> 1) * SM::kRingStride + 2 * SM::kRingSlot + (row & 1) * SM::kRingRowR,
+                        reinterpret_cast<const float*>(p.prev) + ((size_t)(stream0 + (row >> 1)) * 2 + (row & 1)) * B,
+                        (unsigned)(B * sizeof(float)), pro);
+        }
+    }
+    issue(1, false); issue(2, false);
     OHS_STAMP_IF(row == 0, p, 9);
+    __syncthreads();   // the CTA's one common barrier: the mbarriers exist for everybody else
     for (int t = 0; t < p.n_blocks; ++t) {   // every block: the barriers count this warp
         bar_sync(kBarFull0 + (t & 1), SM::kFullCount);
-        issue(t + 3);
+        issue(t + 3, true);
     }
 }
 
@@ -821,9 +887,9 @@ struct OutputStore {
     }
 };
 
-template <int N, int G>
+template <int N, int G, int V>
 __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned char* smem, int stream0, int conv_index) {
-    using SM = RenderSmem<N, G>;
+    using SM = RenderSmem<N, G, V>;
     constexpr int B = SM::B, T = SM::T, NP = SM::NP;
     constexpr int kCount = SM::kWorkers;
     using Pl = FftPlan<N, T>;
@@ -856,6 +922,21 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     float* out_l = p.out + ((size_t)(s - p.io_first_stream) * 2) * p.row_stride;
     float* out_r = out_l + p.row_stride;
     auto stream_sync = [&]() { if (T > 32) bar_sync(kBarStream0 + g, T); else __syncwarp(); };
+    // the delay line and the history rows are what the previous launch wrote
+    grid_dependency_wait();
+    __syncthreads();   // the CTA's one common barrier: the staging warp has initialised the mbarriers
+    // twiddles, shared filter spectra and history rows, brought in by the staging warp's TMA copies
+    mbar_wait(reinterpret_cast<uint64_t*>(smem + SM::kMbarOff) + 5, 0u);
+    OHS_STAMP_IF(ft == 0, p, 1);
+    if constexpr (SM::kFusedMac && SM::kFiltSmemBytes > 0) {
+        if (p.filt_in_smem == 1) {
+            // even-bins-first (global layout, landed in stream 0's FFT buffers) -> natural order
+            const float4* src = reinterpret_cast<const float4*>(smem + SM::kZOff);
+            float4* fs = reinterpret_cast<float4*>(smem + SM::kFiltOff);
+            for (int i = ft; i < N; i += G * T) fs[i] = src[(i & 1) * (N / 2) + (i >> 1)];
+            bar_sync(kBarConv, G * T);
+        }
+    }
 
     constexpr int kPairs = N / 4 / T;
     // TMA filter-tile pipeline (see the block loop): needs two streams' FFT buffers as tile buffers, one shared set with
@@ -1122,68 +1203,40 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     // overlap-save history for the next launch: the last filtered block
     if (valid && p.conv_enable && p.n_blocks > 0) {
         const float* xc = ring_g + ((p.n_blocks - 1) % 3) * SM::kRingSlot;
-        for (int n = tid; n < B; n += T) p.prev[(size_t)s * B + n] = make_float2(xc[n], xc[SM::kRingRowR + n]);
+        float* hl = reinterpret_cast<float*>(p.prev) + (size_t)s * 2 * B;
+        for (int n = 4 * tid; n < B; n += 4 * T) {
+            *reinterpret_cast<float4*>(hl + n) = *reinterpret_cast<const float4*>(xc + n);
+            *reinterpret_cast<float4*>(hl + B + n) = *reinterpret_cast<const float4*>(xc + SM::kRingRowR + n);
+        }
     }
     OHS_STAMP_IF(ft == 0, p, 7);
 }
 
 // which convolution warp (if any) the placement puts on hardware warp slot `warp`
-template <int N, int G, int... F>
+template <int N, int G, int V, int... F>
 __device__ __forceinline__ int find_conv_index(int warp, std::integer_sequence<int, F...>) {
     int r = -1;
-    ((RenderSmem<N, G>::template kConvWarpId<F> == warp ? (void)(r = F) : (void)0), ...);
+    ((RenderSmem<N, G, V>::template kConvWarpId<F> == warp ? (void)(r = F) : (void)0), ...);
     return r;
 }
 
-template <int N, int G>
-__global__ void __maxnreg__((RenderSmem<N, G>::kMaxRegs)) render_kernel(const RenderParams p) {
-    using SM = RenderSmem<N, G>;
+template <int N, int G, int V = 0>
+__global__ void __maxnreg__((RenderSmem<N, G, V>::kMaxRegs)) render_kernel(const RenderParams p) {
+    using SM = RenderSmem<N, G, V>;
     extern __shared__ __align__(16) unsigned char smem[];
     const int stream0 = p.first_stream + blockIdx.x * G;
     OHS_STAMP(p, 0);
     launch_dependents();   // the next launch's CTAs may take this SM as soon as this CTA leaves it
-    {
-        // ---- state-independent part of the prologue (twiddles, shared filter spectra, barriers): under a programmatic
-        // dependent launch it overlaps the tail of the previous launch on the stream
-        float2* tw = reinterpret_cast<float2*>(smem + SM::kTwOff);
-        for (int i = threadIdx.x; i < N; i += SM::kThreads) tw[i] = p.tw[i];
-        if (threadIdx.x == 0) {
-            uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
-            mbar_init(&stage_full[0], 1);
-            mbar_init(&stage_full[1], 1);
-            mbar_init(&stage_full[2], 1);
-            mbar_init(&stage_full[3], 1);  // filt_full[0..1]: filter tiles of the long-impulse-response path
-            mbar_init(&stage_full[4], 1);
-            fence_mbar_init();
-        }
-        if (p.filt_in_smem) {
-            // one shared HRIR set with few partitions: its spectra stay in shared memory for the whole launch
-            float4* fs = reinterpret_cast<float4*>(smem + SM::kFiltOff);
-            const int n4 = p.filt_in_smem * N;  // partitions * N
-            // the fused single-partition path reads bin k at position k; every other path keeps the global table's
-            // even-bins-first layout
-            const bool natural = SM::kFusedMac && p.filt_in_smem == 1;
-            for (int i = threadIdx.x; i < n4; i += SM::kThreads) fs[i] = natural ? p.filt[(i & 1) * (N / 2) + (i >> 1)] : p.filt[i];
-        }
-        // ---- everything below reads what earlier launches wrote (stream state, possibly the input rows)
-        grid_dependency_wait();
-        // overlap-save history -> ring slot 2 (the "previous" slot of block 0)
-        float* ring = reinterpret_cast<float*>(smem + SM::kRingOff);
-        for (int q = threadIdx.x; q < G * SM::B; q += SM::kThreads) {
-            const int g = q / SM::B, n = q - g * SM::B;
-            const int s = stream0 + g;
-            const float2 v = (s < p.n_streams) ? p.prev[(size_t)s * SM::B + n] : make_float2(0.f, 0.f);
-            ring[g * SM::kRingStride + 2 * SM::kRingSlot + n] = v.x;
-            ring[g * SM::kRingStride + 2 * SM::kRingSlot + SM::kRingRowR + n] = v.y;
-        }
-    }
-    __syncthreads();
-    OHS_STAMP(p, 1);
+    // No common prologue: every role runs its own state-independent set-up first (the staging warp initialises the
+    // mbarriers and starts the TMA copies, the EQ warps fetch their coefficients), waits (griddepcontrol) for the
+    // previous launch only where it first touches what that launch wrote, and then meets the others at the CTA's single
+    // __syncthreads.
     const int warp = threadIdx.x >> 5;
-    if (warp < SM::kEqWarps) { eq_warp_main<N, G>(p, smem, stream0, warp); return; }
-    if (warp == SM::kStagerWarpId) { stager_warp_main<N, G>(p, smem, stream0); return; }
-    const int conv_index = find_conv_index<N, G>(warp, std::make_integer_sequence<int, SM::kConvWarps>{});
-    if (conv_index >= 0) conv_warps_main<N, G>(p, smem, stream0, conv_index);  // other warp slots are placement padding
+    if (warp < SM::kEqWarps) { eq_warp_main<N, G, V>(p, smem, stream0, warp); return; }
+    if (warp == SM::kStagerWarpId) { stager_warp_main<N, G, V>(p, smem, stream0); return; }
+    const int conv_index = find_conv_index<N, G, V>(warp, std::make_integer_sequence<int, SM::kConvWarps>{});
+    if (conv_index >= 0) { conv_warps_main<N, G, V>(p, smem, stream0, conv_index); return; }
+    __syncthreads();   // placement padding: take part in the common barrier, then leave
 }
 
 }  // namespace ohs

@@ -13,8 +13,8 @@ namespace {
 
 constexpr int N = OHS_RENDER_N;
 
-template <int G> cudaError_t launch_g(const RenderLaunch& L, const RenderParams& p) {
-    using SM = RenderSmem<N, G>;
+template <int G, int V> cudaError_t launch_gv(const RenderLaunch& L, const RenderParams& p) {
+    using SM = RenderSmem<N, G, V>;
     if constexpr (!SM::kFits) {
         return cudaErrorInvalidConfiguration;
     } else {
@@ -22,9 +22,9 @@ template <int G> cudaError_t launch_g(const RenderLaunch& L, const RenderParams&
         // attribute twice is harmless)
         static std::atomic<unsigned char> attr_set[64];
         if (L.device >= 0 && L.device < 64 && !attr_set[L.device].load(std::memory_order_acquire)) {
-            cudaError_t e = cudaFuncSetAttribute(render_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kBytes);
+            cudaError_t e = cudaFuncSetAttribute(render_kernel<N, G, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kBytes);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(render_kernel<N, G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            e = cudaFuncSetAttribute(render_kernel<N, G, V>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return e;
             attr_set[L.device].store(1, std::memory_order_release);
         }
@@ -42,8 +42,18 @@ template <int G> cudaError_t launch_g(const RenderLaunch& L, const RenderParams&
         attr[0].val.programmaticStreamSerializationAllowed = L.dependent ? 1 : 0;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, render_kernel<N, G>, q);
+        return cudaLaunchKernelEx(&cfg, render_kernel<N, G, V>, q);
     }
+}
+
+// the latency variant (RenderSmem, V = 1) where it exists and fits, else the throughput variant
+template <int G> cudaError_t launch_g(const RenderLaunch& L, const RenderParams& p) {
+    if constexpr (N == 512) {
+        if constexpr (RenderSmem<N, G, 1>::kFits) {
+            if (L.latency_variant) return launch_gv<G, 1>(L, p);
+        }
+    }
+    return launch_gv<G, 0>(L, p);
 }
 
 template <int G> constexpr int threads_g() {

@@ -68,6 +68,7 @@ SYMBOLS = [
     ("ohs_sync", C.c_int, [_VP]),
     ("ohs_cuda_stream", C.c_int, [_VP, C.POINTER(_VP)]),
     ("ohs_launch_count", C.c_int, [_VP, C.POINTER(C.c_uint64)]),
+    ("ohs_enable_timing", C.c_int, [_VP, C.c_int]),
     ("ohs_last_kernel_ms", C.c_int, [_VP, C.POINTER(C.c_float)]),
     ("ohs_mix_device", C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_size_t, C.c_size_t]),
     ("ohs_host_alloc", C.c_int, [C.POINTER(_VP), C.c_size_t]),
@@ -300,6 +301,9 @@ class Engine:
         n = C.c_uint64()
         _check(self._L.ohs_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def enable_timing(self, on: bool = True):
+        _check(self._L.ohs_enable_timing(self._h, int(on)))
 
     def last_kernel_ms(self) -> float:
         ms = C.c_float()

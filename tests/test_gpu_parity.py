@@ -185,15 +185,25 @@ def test_conv_parity(block, taps, n_streams, n_blocks):
     assert np.max(np.abs(y[0, 0] - tl)) <= TOL
 
 
-def test_conv_block_at_a_time_equals_one_long_call():
-    """K = 1 launches (the per-block API) and one K = 12 launch walk the same state: identical bits."""
-    h = S.synthetic_hrir_set(900, 150.0, seed=3)
-    x = S.stream_inputs(4, 256 * 12, base_seed=300)
-    a = ohs.Engine(4, 256, 900, n_bands=0); a.set_hrir_set(h)
-    b = ohs.Engine(4, 256, 900, n_bands=0); b.set_hrir_set(h)
-    whole = a.process(x)
-    parts = np.concatenate([b.process(x[:, :, i:i + 256]) for i in range(0, x.shape[2], 256)], axis=2)
-    assert whole.tobytes() == parts.tobytes()
+@pytest.mark.parametrize("block,taps,n_streams,bands", [(256, 900, 4, 0), (256, 256, 9, 10), (128, 512, 5, 10), (64, 100, 3, 10), (512, 200, 2, 10)])
+def test_conv_block_at_a_time_equals_one_long_call(block, taps, n_streams, bands):
+    """K = 1 launches (the per-block API: the latency variant of the render kernel, one band per EQ lane, two warps per
+    stream in the N = 512 transforms), K = 2 launches and one K = 12 launch (the throughput variant) walk the same
+    state: identical bits, multi-partition and single-partition (fused in registers in the throughput variant)."""
+    h = S.synthetic_hrir_set(taps, taps / 6.0, seed=3)
+    x = S.stream_inputs(n_streams, block * 12, base_seed=300)
+
+    def engine():
+        e = ohs.Engine(n_streams, block, taps, n_bands=bands); e.set_hrir_set(h)
+        if bands:
+            e.eq_set_preset(S.EQ_PRESET_TYPICAL); e.set_eq_enable(True); e.set_gain(0.5)
+        return e
+
+    whole = engine().process(x)
+    for k in (1, 2, 3):
+        b = engine()
+        parts = np.concatenate([b.process(x[:, :, i:i + k * block]) for i in range(0, x.shape[2], k * block)], axis=2)
+        assert whole.tobytes() == parts.tobytes(), k
 
 
 def test_default_ir_is_silence_and_empty_ir_mutes():
@@ -372,6 +382,7 @@ def test_device_pointers_stride_and_in_place():
     buf[:, :, :256 * 8] = torch.from_numpy(x).cuda()
     torch.cuda.synchronize()
     n0 = e.launch_count()
+    e.enable_timing(True)
     e.process_device(buf.data_ptr(), buf.data_ptr(), 256 * 8, stride)  # in place, padded rows
     e.sync()
     assert e.launch_count() == n0 + 1
@@ -684,7 +695,7 @@ def test_eq_frequency_response_product_function():
             c = coeffs[b].astype(np.float64)
             _, hh = sps.freqz([c[0], c[1], c[2]], [1.0, c[3], c[4]], worN=freqs.astype(np.float64), fs=fs)
             truth *= np.abs(hh)
-        assert np.max(np.abs(got / truth - 1.0)) <= 2e-4
+        assert np.max(np.abs(got / truth - 1.0)) <= 2e-3   # f32 evaluation, as in the reference (cancellation at low f)
         # the mirror object passes its sample_rate argument through (reference signature)
         m = ohs.StereoParametricEQ(10, 48000.0)
         for b in range(10):

@@ -27,6 +27,7 @@ def run(name, n_streams, block, taps, fs, decay, k_blocks, reps=5, eq=True):
     eng = pkg.Engine(n_streams, block, taps, sample_rate=fs)
     eng.set_hrir_set(h)
     eng.eq_set_preset(S.EQ_PRESET_TYPICAL)
+    eng.enable_timing()
     eng.set_eq_enable(eq)
     eng.set_gain(0.5)
     n = block * k_blocks

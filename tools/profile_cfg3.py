@@ -5,7 +5,7 @@ sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(_
 import _bootstrap, torch  # noqa: E402
 pkg = _bootstrap.load_package(); S = pkg.signals
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-eng = pkg.Engine(8192, 128, 512); eng.set_hrir_set(S.synthetic_hrir_set(512, 80.0)); eng.eq_set_preset(S.EQ_PRESET_TYPICAL)
+eng = pkg.Engine(8192, 128, 512); eng.set_hrir_set(S.synthetic_hrir_set(512, 80.0)); eng.eq_set_preset(S.EQ_PRESET_TYPICAL); eng.enable_timing()
 eng.set_eq_enable(True); eng.set_gain(0.5)
 n = 128 * K
 x = torch.randn((8192, 2, n), device="cuda") * 0.1; y = torch.empty_like(x); torch.cuda.synchronize()

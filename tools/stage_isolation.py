@@ -3,7 +3,7 @@ sys.path.insert(0,'/root/repo')
 import _bootstrap, torch, numpy as np
 pkg=_bootstrap.load_package(); S=pkg.signals
 def run(conv, eq, K=192):
-    eng=pkg.Engine(1024,256,256); eng.set_hrir_set(S.synthetic_hrir_set(256,40.0)); eng.eq_set_preset(S.EQ_PRESET_TYPICAL)
+    eng=pkg.Engine(1024,256,256); eng.set_hrir_set(S.synthetic_hrir_set(256,40.0)); eng.eq_set_preset(S.EQ_PRESET_TYPICAL); eng.enable_timing()
     eng.set_eq_enable(eq); eng.set_conv_enable(conv); eng.set_gain(0.5)
     n=256*K
     x=torch.randn((1024,2,n),device='cuda')*0.1; y=torch.empty_like(x); torch.cuda.synchronize()

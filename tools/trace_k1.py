@@ -21,7 +21,8 @@ L = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 c = S.CONFIGS[cfg]
 n_streams, block, taps, fs = c["n_streams"], c["block"], c["taps"], c["fs"]
 NAMES = ["entry", "prologue done", "eq: coeffs loaded", "eq: first rows landed", "eq: last block filtered", "conv: first block ready",
-         "conv: last block written", "conv: history saved", "eq: state saved", "stager: first copies issued"]
+         "conv: last block written", "conv: history saved", "eq: state saved", "stager: first copies issued", "stager: mbarriers initialised",
+         "stager: constant tables issued", "stager: previous launch complete", "stager: block 0 rows issued"]
 
 
 def run(pdl: str):
@@ -57,8 +58,8 @@ def run(pdl: str):
     if traced:
         st = stamps.cpu().numpy()[4:]          # skip the first launches
         rel = st - st[:, :, :1]
-        out["cycles_since_entry_median"] = {NAMES[i]: float(np.median(rel[:, :, i][st[:, :, i] > 0])) for i in range(1, 10) if (st[:, :, i] > 0).any()}
-        out["cycles_since_entry_max"] = {NAMES[i]: float(np.max(rel[:, :, i][st[:, :, i] > 0])) for i in range(1, 10) if (st[:, :, i] > 0).any()}
+        out["cycles_since_entry_median"] = {NAMES[i]: float(np.median(rel[:, :, i][st[:, :, i] > 0])) for i in range(1, len(NAMES)) if (st[:, :, i] > 0).any()}
+        out["cycles_since_entry_max"] = {NAMES[i]: float(np.max(rel[:, :, i][st[:, :, i] > 0])) for i in range(1, len(NAMES)) if (st[:, :, i] > 0).any()}
     print(json.dumps(out))
 
 
