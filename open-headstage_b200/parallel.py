@@ -84,46 +84,86 @@ def reduce_bus(bus: torch.Tensor, dst: int = 0, group=None) -> torch.Tensor:
     return bus
 
 
+class ObjectMixer:
+    """BASELINE config 4 on this rank's share.  `hrirs` [n_src, 2, taps] (left-ear, right-ear impulse responses of each
+    source's direction, n_src even).  Two sources ride in one stereo stream of the engine (source 2i on the left input
+    with paths LSL/LSR, source 2i+1 on the right input with RSL/RSR); render() sums the rendered streams into this
+    rank's stereo bus on the GPU, the buses are summed onto rank `dst` with NCCL, and the EQ and the output gain are
+    applied ONCE to the reduced bus there (the definition of SURVEY.md §8e — the reference has no multi-source mode).
+
+    All set-up (engine, one HRIR set per stream, filter transforms, scratch) happens in the constructor; render() holds
+    only the data path: process -> mix -> reduce -> bus EQ."""
+
+    def __init__(self, pkg, hrirs, block: int, fs: float, n_frames: int, eq_preset=None, gain: float = 1.0, device: int = 0,
+                 dst: int = 0, group=None):
+        import numpy as np
+
+        n_src, two, taps = hrirs.shape
+        assert two == 2 and n_src % 2 == 0 and n_frames % block == 0 and n_frames % 4 == 0
+        self.n_src, self.n_streams, self.n_frames, self.block, self.dst, self.group = n_src, n_src // 2, n_frames, block, dst, group
+        self.device = torch.device("cuda", device)
+        hrirs = np.ascontiguousarray(hrirs, dtype=np.float32)
+        self.engine = eng = pkg.Engine(self.n_streams, block, taps, n_bands=0, n_hrir_sets=self.n_streams, device=device, sample_rate=fs)
+        for i in range(self.n_streams):
+            eng.set_ir(0, hrirs[2 * i, 0], hrir_set=i)      # LSL: source 2i   -> left ear
+            eng.set_ir(1, hrirs[2 * i, 1], hrir_set=i)      # LSR: source 2i   -> right ear
+            eng.set_ir(2, hrirs[2 * i + 1, 0], hrir_set=i)  # RSL: source 2i+1 -> left ear
+            eng.set_ir(3, hrirs[2 * i + 1, 1], hrir_set=i)  # RSR: source 2i+1 -> right ear
+            eng.bind_stream_hrir(i, i)
+        eng.prepare(n_frames)                                # one upload + one transform launch for all the sets
+        self.rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+        self.post = None
+        if self.rank == dst and (eq_preset is not None or gain != 1.0):
+            self.post = post = pkg.Engine(1, block, 1, n_bands=10, device=device, sample_rate=fs)
+            post.set_conv_enable(False)
+            if eq_preset is not None:
+                post.eq_set_preset(eq_preset)
+                post.set_eq_enable(True)
+            post.set_gain(gain)
+            post.prepare(n_frames)
+        with torch.cuda.device(self.device):
+            self.rendered = torch.empty((self.n_streams, 2, n_frames), dtype=torch.float32, device=self.device)
+            self.bus = torch.zeros((2, n_frames), dtype=torch.float32, device=self.device)
+            self._eng_stream = torch.cuda.ExternalStream(eng.cuda_stream(), device=self.device)
+            self._post_stream = torch.cuda.ExternalStream(self.post.cuda_stream(), device=self.device) if self.post else None
+        eng.sync()
+
+    def reset(self):
+        self.engine.conv_reset()
+        if self.post:
+            self.post.eq_reset()
+
+    def render(self, sources: torch.Tensor, apply_post: bool = True):
+        """sources [n_src, n_frames] f32 on this rank's GPU (viewed as [n_streams, 2, n_frames]).  Returns the reduced,
+        equalised [2, n_frames] bus on rank `dst` (valid after torch.cuda.synchronize()), None elsewhere.
+        apply_post=False leaves the reduced bus raw (no EQ, no gain)."""
+        assert sources.is_cuda and sources.dtype == torch.float32 and sources.is_contiguous() and tuple(sources.shape) == (self.n_src, self.n_frames)
+        eng = self.engine
+        cur = torch.cuda.current_stream(self.device)
+        self._eng_stream.wait_stream(cur)
+        eng.process_device(sources.data_ptr(), self.rendered.data_ptr(), self.n_frames)
+        eng.mix_device(self.rendered.data_ptr(), self.bus.data_ptr(), self.n_frames)
+        cur.wait_stream(self._eng_stream)
+        reduce_bus(self.bus, dst=self.dst, group=self.group)        # NCCL, on torch's current stream
+        if self.rank != self.dst:
+            return None
+        if self.post and apply_post:
+            self._post_stream.wait_stream(cur)
+            self.post.process_device(self.bus.data_ptr(), self.bus.data_ptr(), self.n_frames)
+            cur.wait_stream(self._post_stream)
+        return self.bus
+
+
 def render_object_mix(pkg, sources, hrirs, block: int, fs: float, eq_preset=None, gain: float = 1.0, device: int = 0,
                       src: int = 0, group=None):
-    """BASELINE config 4 on this rank's share: `sources` [n_src, n_frames] mono signals (n_src even), `hrirs`
-    [n_src, 2, taps] (left-ear, right-ear impulse responses of each source's direction).  Two sources ride in one stereo
-    stream of the engine (source 2i on the left input with paths LSL/LSR, source 2i+1 on the right input with RSL/RSR);
-    the rendered streams are summed into this rank's stereo bus on the GPU, the buses are summed onto rank `src` with
-    NCCL, and the EQ and the output gain are applied ONCE to the reduced bus there (the definition of SURVEY.md §8e —
-    the reference has no multi-source mode).  Returns the [2, n_frames] bus (torch, CUDA) on `src`, None elsewhere."""
+    """One-shot form of ObjectMixer: `sources` [n_src, n_frames] mono signals on the host.  Returns the [2, n_frames] bus
+    (torch, CUDA) on rank `src`, None elsewhere."""
     import numpy as np
 
     n_src, n_frames = sources.shape
-    assert n_src % 2 == 0 and n_frames % block == 0 and n_frames % 4 == 0
-    taps = hrirs.shape[2]
-    n_streams = n_src // 2
-    eng = pkg.Engine(n_streams, block, taps, n_bands=0, n_hrir_sets=n_streams, device=device, sample_rate=fs)
-    for i in range(n_streams):
-        eng.set_ir(0, hrirs[2 * i, 0], hrir_set=i)      # LSL: source 2i   -> left ear
-        eng.set_ir(1, hrirs[2 * i, 1], hrir_set=i)      # LSR: source 2i   -> right ear
-        eng.set_ir(2, hrirs[2 * i + 1, 0], hrir_set=i)  # RSL: source 2i+1 -> left ear
-        eng.set_ir(3, hrirs[2 * i + 1, 1], hrir_set=i)  # RSR: source 2i+1 -> right ear
-        eng.bind_stream_hrir(i, i)
-    x = torch.from_numpy(np.ascontiguousarray(sources.reshape(n_streams, 2, n_frames), dtype=np.float32)).to("cuda:%d" % device)
-    y = torch.empty_like(x)
-    bus = torch.zeros((2, n_frames), dtype=torch.float32, device=x.device)
-    torch.cuda.synchronize(x.device)
-    eng.process_device(x.data_ptr(), y.data_ptr(), n_frames)
-    eng.mix_device(y.data_ptr(), bus.data_ptr(), n_frames)
-    eng.sync()
-    reduce_bus(bus, dst=src, group=group)
-    rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
-    if rank != src:
-        return None
-    if eq_preset is not None or gain != 1.0:
-        post = pkg.Engine(1, block, 1, n_bands=10, device=device, sample_rate=fs)
-        post.set_conv_enable(False)
-        if eq_preset is not None:
-            post.eq_set_preset(eq_preset)
-            post.set_eq_enable(True)
-        post.set_gain(gain)
-        torch.cuda.synchronize(x.device)
-        post.process_device(bus.data_ptr(), bus.data_ptr(), n_frames)
-        post.sync()
-    return bus
+    mixer = ObjectMixer(pkg, hrirs, block, fs, n_frames, eq_preset=eq_preset, gain=gain, device=device, dst=src, group=group)
+    x = torch.from_numpy(np.ascontiguousarray(sources, dtype=np.float32)).to(mixer.device)
+    torch.cuda.synchronize(mixer.device)
+    bus = mixer.render(x)
+    torch.cuda.synchronize(mixer.device)
+    return bus.clone() if bus is not None else None

@@ -35,15 +35,38 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def build_native() -> str:
+    """The same source built -march=native into oracle/_native/ (git-ignored) on the machine that will TIME it — the
+    CPU-baseline legs of bench.py only; the parity tests keep the portable build that travels with the repo."""
+    out_dir = os.path.join(_HERE, "_native")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "libohs_oracle_native.so")
+    src = os.path.join(_HERE, "ohs_oracle.c")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        tmp = out + ".tmp.%d" % os.getpid()
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-std=gnu11", "-shared",
+                               "-o", tmp, src, "-lm", "-lpthread"], cwd=_HERE)
+        os.replace(tmp, out)
+    return out
+
+
 _lib = None
+_lib_path = _LIB_PATH
+
+
+def use_library(path: str) -> None:
+    """Bind this module to another build of the oracle (build_native()); call before the first use."""
+    global _lib, _lib_path
+    if path != _lib_path:
+        _lib, _lib_path = None, path
 
 
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
+        if _lib_path == _LIB_PATH and not os.path.exists(_LIB_PATH):
             build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(_lib_path)
         L.oracle_conv_new.restype = C.c_void_p
         L.oracle_conv_new.argtypes = [C.c_int]
         L.oracle_conv_free.argtypes = [C.c_void_p]
