@@ -250,8 +250,12 @@ class Ctx:
             raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        self.comm = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
+            # the data path's two collectives (spectra broadcast, config-4 bus reduce) go through the C ABI's own NCCL
+            # communicator; torch.distributed is plumbing (rendezvous, barriers, max-over-ranks)
+            self.comm = pkg.parallel.create_comm(pkg, self.local)
 
     def barrier(self):
         if self.world > 1:
@@ -326,7 +330,7 @@ def run_stream_config(ctx: Ctx, cfg_id: int, k_blocks: int, reps: int):
     if ctx.rank == 0 or ctx.world == 1:
         eng.set_hrir_set(h)
     if ctx.world > 1:
-        pkg.parallel.broadcast_filters(eng, src=0)      # the spectra table of the whole job comes from rank 0
+        pkg.parallel.broadcast_filters(eng, src=0, comm=ctx.comm)   # the spectra table of the whole job comes from rank 0
     for b in range(10):
         eng.eq_set_band(b, coeffs[b], True)
     eng.set_eq_enable(True); eng.set_gain(GAIN)
@@ -385,7 +389,7 @@ def run_object_config(ctx: Ctx, reps: int):
     for s in range(n_src):
         src[s] = d_base[s % 8] * float(sign(s))
     t_setup = time.perf_counter()
-    mixer = P.ObjectMixer(pkg, hr, block, fs, n, eq_preset=S.EQ_PRESET_TYPICAL, gain=GAIN, device=ctx.local, dst=0)
+    mixer = P.ObjectMixer(pkg, hr, block, fs, n, eq_preset=S.EQ_PRESET_TYPICAL, gain=GAIN, device=ctx.local, dst=0, comm=ctx.comm)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
     # parity on the first 19 blocks (4864 frames): f64 truth of this rank's sources, summed over ranks like the bus
@@ -447,7 +451,7 @@ def run_gpu(args, pkg):
         eng.sync()
     if world > 1:
         # one HRIR spectra table for the whole job: rank 0 transforms the IRs, NCCL broadcasts the spectra
-        pkg.parallel.broadcast_filters(eng, src=0)
+        pkg.parallel.broadcast_filters(eng, src=0, comm=ctx.comm)
     for b in range(10):
         eng.eq_set_band(b, coeffs[b], True)
     eng.set_eq_enable(True)

@@ -47,7 +47,8 @@ typedef enum ohs_status {
     OHS_ERR_NO_DEVICE = -3,   /* no usable CUDA device (no CPU fallback exists) */
     OHS_ERR_NYQUIST = -4,     /* EQ design: 2*fc > fs  (biquad Errors::OutsideNyquist) */
     OHS_ERR_NEGATIVE_Q = -5,  /* EQ design: q < 0      (biquad Errors::NegativeQ) */
-    OHS_ERR_ALIGNMENT = -6    /* device/host audio pointer or row stride not 16-byte aligned */
+    OHS_ERR_ALIGNMENT = -6,   /* device/host audio pointer or row stride not 16-byte aligned */
+    OHS_ERR_NCCL = -7         /* libnccl could not be opened, or an NCCL call failed; message holds ncclGetErrorString */
 } ohs_status;
 
 /* src/dsp/convolution.rs:26-33  enum ConvolutionPath { Lsl, Lsr, Rsl, Rsr }
@@ -176,6 +177,25 @@ int ohs_last_kernel_ms(ohs_engine* h, float* ms);
  * (src/dsp/convolution.rs:229-230).  n_frames must be a multiple of 4; pointers 16-byte aligned.  Enqueues on the
  * engine's stream.  The per-GPU buses are then summed with NCCL (parallel.reduce_bus). */
 int ohs_mix_device(ohs_engine* h, const float* d_in, float* d_bus, size_t n_frames, size_t row_stride, size_t bus_stride);
+
+/* ---- multi-GPU collectives -------------------------------------------------------------------------
+ * Streams shard across GPUs with no data-path collective; NCCL is used for exactly two things, both available here so
+ * that a host without Python has the N > 1 path: one HRIR spectra table for the whole job (set_ir runs on one rank
+ * only) and, for the object mixdown (config 4), the sum of the per-GPU stereo buses.  libnccl.so.2 is opened at run
+ * time (dlopen) by the first ohs_comm_* call; a process that never calls them does not need NCCL.
+ * One rank obtains the 128-byte id (ncclGetUniqueId) and ships it to the others by any means (the reference has no
+ * multi-process mode; under torchrun parallel.create_comm ships it with torch.distributed). */
+typedef struct ohs_comm ohs_comm;
+#define OHS_COMM_ID_BYTES 128
+int ohs_comm_unique_id(void* id128);
+int ohs_comm_create(ohs_comm** out, int world, int rank, int device, const void* id128);   /* ncclCommInitRank */
+int ohs_comm_destroy(ohs_comm* c);
+/* Rank `root` uploads its pending set_ir work and broadcasts the device-resident spectra table and the per-set partition
+ * counts on the engine's stream; the other ranks' sets are marked as externally filled (ohs_mark_filters_external).
+ * Returns after the stream has drained. */
+int ohs_broadcast_hrir(ohs_engine* h, ohs_comm* c, int root);
+/* In-place ncclReduce(sum) of d_bus[n_floats] onto rank `root`, enqueued on the engine's stream (after ohs_mix_device). */
+int ohs_reduce_bus(ohs_engine* h, ohs_comm* c, float* d_bus, size_t n_floats, int root);
 
 /* pinned host memory helpers */
 int ohs_host_alloc(void** p, size_t bytes);

@@ -9,5 +9,5 @@ from . import autoeq, parallel, signals, sofa  # noqa: F401
 from ._build import build_host_tests, build_library  # noqa: F401
 from .engine import (  # noqa: F401
     ALLPASS, BANDPASS, HIGHPASS, HIGHSHELF, LOWPASS, LOWSHELF, LSL, LSR, NOTCH, OHS_ALL, PEAK, RSL, RSR, SYMBOLS,
-    BandConfig, ConvolutionEngine, Engine, OhsError, PinnedBuffer, StereoParametricEQ, eq_design, load_library,
+    BandConfig, Comm, ConvolutionEngine, Engine, OhsError, PinnedBuffer, StereoParametricEQ, comm_unique_id, eq_design, load_library,
 )

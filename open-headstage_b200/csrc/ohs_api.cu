@@ -8,6 +8,8 @@
 #include "../../include/ohs.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library itself is opened with dlopen by the first ohs_comm_* call
 
 #include <algorithm>
 #include <atomic>
@@ -881,6 +883,147 @@ int ohs_mix_device(ohs_engine* h, const float* d_in, float* d_bus, size_t n_fram
     mix_streams_kernel<<<grid, threads, 0, h->stream>>>(d_in, d_bus, h->cfg.n_streams, n_frames, row_stride, bus_stride);
     OHS_CUDA(cudaGetLastError());
     h->launches++;
+    return OHS_OK;
+}
+
+// ---- collectives ----------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+const NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::atomic<int> state{0};   // 0 untried, 1 ready, -1 failed
+    static std::atomic_flag busy = ATOMIC_FLAG_INIT;
+    if (state.load(std::memory_order_acquire) == 0) {
+        while (busy.test_and_set(std::memory_order_acquire)) {}
+        if (state.load(std::memory_order_relaxed) == 0) {
+            // a process that already holds an NCCL (e.g. torch's bundled one) gets that one back by SONAME
+            void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            bool ok = lib != nullptr;
+            auto sym = [&](const char* name) { void* p = lib ? dlsym(lib, name) : nullptr; ok = ok && p; return p; };
+            api.lib = lib;
+            api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+            api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+            api.Reduce = (decltype(api.Reduce))sym("ncclReduce");
+            api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+            api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+            state.store(ok ? 1 : -1, std::memory_order_release);
+        }
+        busy.clear(std::memory_order_release);
+    }
+    return state.load(std::memory_order_acquire) == 1 ? &api : nullptr;
+}
+
+#define OHS_NCCL(api, expr)                                                                                          \
+    do {                                                                                                             \
+        ncclResult_t _r = (expr);                                                                                    \
+        if (_r != ncclSuccess) return fail(OHS_ERR_NCCL, "%s failed: %s", #expr, (api)->GetErrorString(_r));          \
+    } while (0)
+}  // namespace
+
+struct ohs_comm {
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0, device = 0;
+};
+
+int ohs_comm_unique_id(void* id128) {
+    static_assert(sizeof(ncclUniqueId) == OHS_COMM_ID_BYTES, "ncclUniqueId size");
+    if (!id128) return fail(OHS_ERR_INVALID, "null output");
+    const NcclApi* api = nccl_api();
+    if (!api) return fail(OHS_ERR_NCCL, "libnccl.so.2 could not be opened: %s", dlerror() ? dlerror() : "symbol missing");
+    ncclUniqueId id;
+    OHS_NCCL(api, api->GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return OHS_OK;
+}
+
+int ohs_comm_create(ohs_comm** out, int world, int rank, int device, const void* id128) {
+    if (!out || !id128) return fail(OHS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return fail(OHS_ERR_INVALID, "rank %d outside world %d", rank, world);
+    const NcclApi* api = nccl_api();
+    if (!api) return fail(OHS_ERR_NCCL, "libnccl.so.2 could not be opened");
+    OHS_CUDA(cudaSetDevice(device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ohs_comm* c = new ohs_comm();
+    c->world = world; c->rank = rank; c->device = device;
+    ncclResult_t r = api->CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) { delete c; return fail(OHS_ERR_NCCL, "ncclCommInitRank failed: %s", api->GetErrorString(r)); }
+    *out = c;
+    return OHS_OK;
+}
+
+int ohs_comm_destroy(ohs_comm* c) {
+    if (!c) return OHS_OK;
+    const NcclApi* api = nccl_api();
+    if (api && c->comm) { cudaSetDevice(c->device); api->CommDestroy(c->comm); }
+    delete c;
+    return OHS_OK;
+}
+
+int ohs_broadcast_hrir(ohs_engine* h, ohs_comm* c, int root) {
+    OHS_CHECK_HANDLE(h);
+    if (!c) return fail(OHS_ERR_INVALID, "null communicator");
+    if (root < 0 || root >= c->world) return fail(OHS_ERR_INVALID, "root %d outside world %d", root, c->world);
+    if (c->device != h->cfg.device) return fail(OHS_ERR_INVALID, "communicator is on device %d, engine on %d", c->device, h->cfg.device);
+    const NcclApi* api = nccl_api();
+    if (!api) return fail(OHS_ERR_NCCL, "libnccl.so.2 could not be opened");
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    const int n_sets = h->cfg.n_hrir_sets;
+    if (c->rank == root) {
+        int rc = commit_filters(h);
+        if (rc) return rc;
+    } else {
+        int rc = upload_bindings(h);
+        if (rc) return rc;
+    }
+    OHS_NCCL(api, api->GroupStart());
+    OHS_NCCL(api, api->Broadcast(h->d_filt, h->d_filt, h->filt_bytes / sizeof(float), ncclFloat32, root, c->comm, h->stream));
+    OHS_NCCL(api, api->Broadcast(h->d_set_parts, h->d_set_parts, (size_t)n_sets, ncclInt32, root, c->comm, h->stream));
+    OHS_NCCL(api, api->GroupEnd());
+    if (c->rank != root) {
+        OHS_CUDA(cudaMemcpyAsync(h->h_set_parts.data(), h->d_set_parts, sizeof(int) * n_sets, cudaMemcpyDeviceToHost, h->stream));
+        OHS_CUDA(cudaStreamSynchronize(h->stream));
+        for (int s = 0; s < n_sets; ++s) {
+            const int parts = h->h_set_parts[s];
+            if (parts < 1 || parts > h->pmax) return fail(OHS_ERR_INVALID, "received partition count %d for HRIR set %d (capacity %d)", parts, s, h->pmax);
+            for (int p = 0; p < 4; ++p) h->h_path_parts[(size_t)s * 4 + p] = parts;
+            h->set_dirty[s] = 0;
+            h->set_external[s] = 1;
+        }
+        h->any_set_dirty = false;
+        // a freshly received response starts from empty history, like set_ir (src/dsp/convolution.rs:135-138)
+        int rc = clear_history(h, false);
+        if (rc) return rc;
+        h->head = 0;
+    }
+    OHS_CUDA(cudaStreamSynchronize(h->stream));
+    return OHS_OK;
+}
+
+int ohs_reduce_bus(ohs_engine* h, ohs_comm* c, float* d_bus, size_t n_floats, int root) {
+    OHS_CHECK_HANDLE(h);
+    if (!c || !d_bus) return fail(OHS_ERR_INVALID, "null argument");
+    if (root < 0 || root >= c->world) return fail(OHS_ERR_INVALID, "root %d outside world %d", root, c->world);
+    const NcclApi* api = nccl_api();
+    if (!api) return fail(OHS_ERR_NCCL, "libnccl.so.2 could not be opened");
+    OHS_CUDA(cudaSetDevice(h->cfg.device));
+    OHS_NCCL(api, api->Reduce(d_bus, d_bus, n_floats, ncclFloat32, ncclSum, root, c->comm, h->stream));
     return OHS_OK;
 }
 

@@ -71,6 +71,11 @@ SYMBOLS = [
     ("ohs_enable_timing", C.c_int, [_VP, C.c_int]),
     ("ohs_last_kernel_ms", C.c_int, [_VP, C.POINTER(C.c_float)]),
     ("ohs_mix_device", C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_size_t, C.c_size_t]),
+    ("ohs_comm_unique_id", C.c_int, [_VP]),
+    ("ohs_comm_create", C.c_int, [C.POINTER(_VP), C.c_int, C.c_int, C.c_int, _VP]),
+    ("ohs_comm_destroy", C.c_int, [_VP]),
+    ("ohs_broadcast_hrir", C.c_int, [_VP, _VP, C.c_int]),
+    ("ohs_reduce_bus", C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_int]),
     ("ohs_host_alloc", C.c_int, [C.POINTER(_VP), C.c_size_t]),
     ("ohs_host_free", C.c_int, [_VP]),
     ("ohs_state_bytes", C.c_int, [_VP, C.POINTER(C.c_size_t)]),
@@ -126,6 +131,38 @@ def eq_design(filter_type: int, fs: float, fc: float, q: float, gain_db: float) 
     out = np.zeros(5, np.float32)
     _check(load_library().ohs_eq_design(filter_type, fs, fc, q, gain_db, out.ctypes.data_as(_f32p)))
     return out
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI (one rank calls it and ships the 128 bytes to the others)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(load_library().ohs_comm_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """ohs_comm: an NCCL communicator owned by the C ABI library (ohs_broadcast_hrir / ohs_reduce_bus)."""
+
+    def __init__(self, world: int, rank: int, device: int, unique_id: bytes):
+        assert len(unique_id) == COMM_ID_BYTES
+        self._L = load_library()
+        self.world, self.rank, self.device = world, rank, device
+        self._c = _VP()
+        _check(self._L.ohs_comm_create(C.byref(self._c), world, rank, device, unique_id))
+
+    def close(self):
+        if getattr(self, "_c", None):
+            self._L.ohs_comm_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class PinnedBuffer:
@@ -202,6 +239,14 @@ class Engine:
 
     def mark_filters_external(self, hrir_set: int, partitions: int):
         _check(self._L.ohs_mark_filters_external(self._h, hrir_set, partitions))
+
+    def broadcast_hrir(self, comm: "Comm", root: int = 0):
+        """One HRIR spectra table for the whole job: rank `root` has called set_ir, everybody receives (C ABI, NCCL)."""
+        _check(self._L.ohs_broadcast_hrir(self._h, comm._c, root))
+
+    def reduce_bus(self, comm: "Comm", d_bus: int, n_floats: int, root: int = 0):
+        """In-place NCCL sum of the per-GPU buses onto `root`, on the engine's stream (config 4)."""
+        _check(self._L.ohs_reduce_bus(self._h, comm._c, d_bus, n_floats, root))
 
     # ---- EQ
     def eq_update_band(self, band: int, filter_type: int, fc: float, q: float, gain_db: float, enabled: bool = True, eq_set: int = 0):

@@ -42,10 +42,25 @@ def set_partition_counts(engine, hrir_sets) -> list[int]:
     return [max(engine.num_partitions(p, s) for p in range(4)) for s in hrir_sets]
 
 
-def broadcast_filters(engine, src: int = 0, hrir_sets=None, group=None) -> None:
+def create_comm(pkg, device: int, group=None):
+    """An ohs_comm (NCCL communicator owned by the C ABI library) over the ranks of the torch.distributed job: rank 0
+    asks NCCL for the unique id through the C ABI, torch.distributed only ships the 128 bytes."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ids = [pkg.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(ids, src=0, group=group)
+    return pkg.Comm(world, rank, device, ids[0])
+
+
+def broadcast_filters(engine, src: int = 0, hrir_sets=None, group=None, comm=None) -> None:
     """Rank `src` must already have called set_ir for `hrir_sets` (default: every set of the engine); the other ranks
     receive the whole device-resident spectra table and, per set, the partition count rank `src` derived from its
-    impulse responses."""
+    impulse responses.  With `comm` (create_comm) the whole exchange is the C ABI's ohs_broadcast_hrir; without it the
+    table is viewed as a torch tensor and torch.distributed broadcasts it."""
+    if comm is not None:
+        engine.broadcast_hrir(comm, src)
+        return
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     sets = list(range(engine.n_hrir_sets)) if hrir_sets is None else [int(s) for s in hrir_sets]
     dev = torch.device("cuda", engine.device)
@@ -95,8 +110,10 @@ class ObjectMixer:
     only the data path: process -> mix -> reduce -> bus EQ."""
 
     def __init__(self, pkg, hrirs, block: int, fs: float, n_frames: int, eq_preset=None, gain: float = 1.0, device: int = 0,
-                 dst: int = 0, group=None):
+                 dst: int = 0, group=None, comm=None):
         import numpy as np
+
+        self.comm = comm   # create_comm(): the bus reduce is then the C ABI's ohs_reduce_bus on the engine's stream
 
         n_src, two, taps = hrirs.shape
         assert two == 2 and n_src % 2 == 0 and n_frames % block == 0 and n_frames % 4 == 0
@@ -143,8 +160,12 @@ class ObjectMixer:
         self._eng_stream.wait_stream(cur)
         eng.process_device(sources.data_ptr(), self.rendered.data_ptr(), self.n_frames)
         eng.mix_device(self.rendered.data_ptr(), self.bus.data_ptr(), self.n_frames)
-        cur.wait_stream(self._eng_stream)
-        reduce_bus(self.bus, dst=self.dst, group=self.group)        # NCCL, on torch's current stream
+        if self.comm is not None:
+            eng.reduce_bus(self.comm, self.bus.data_ptr(), self.bus.numel(), self.dst)   # NCCL, on the engine's stream
+            cur.wait_stream(self._eng_stream)
+        else:
+            cur.wait_stream(self._eng_stream)
+            reduce_bus(self.bus, dst=self.dst, group=self.group)    # NCCL, on torch's current stream
         if self.rank != self.dst:
             return None
         if self.post and apply_post:

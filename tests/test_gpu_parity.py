@@ -797,3 +797,27 @@ def test_state_blob_validation_and_fifo_residue():
         c.state_import(b"\0" * len(blob))
     with pytest.raises(ValueError):
         c.process(np.zeros((2, 2, 256), np.float32), out=np.zeros((2, 2, 256), np.float64))
+
+
+def test_c_abi_collectives_single_rank():
+    """ohs_comm_* / ohs_broadcast_hrir / ohs_reduce_bus on a one-rank NCCL communicator: the calls a multi-GPU host makes,
+    exercised on the single GPU the test box has (the N = 2..8 runs of bench.py use the same entry points)."""
+    import torch
+    from open_headstage_b200 import parallel as P
+
+    comm = P.create_comm(ohs, 0)
+    assert (comm.world, comm.rank) == (1, 0)
+    h = S.synthetic_hrir_set(700, 100.0, seed=5)
+    x = S.stream_inputs(3, 256 * 6, base_seed=2100)
+    a = ohs.Engine(3, 256, 700, n_bands=0); a.set_hrir_set(h)
+    want = a.process(x)
+    b = ohs.Engine(3, 256, 700, n_bands=0); b.set_hrir_set(h)
+    P.broadcast_filters(b, src=0, comm=comm)            # root: commit + broadcast to itself
+    assert b.process(x).tobytes() == want.tobytes()
+    bus = torch.arange(2 * 1024, dtype=torch.float32, device="cuda").reshape(2, 1024).contiguous()
+    keep = bus.clone()
+    b.reduce_bus(comm, bus.data_ptr(), bus.numel(), 0); b.sync()
+    assert torch.equal(bus, keep)                        # sum over one rank
+    with pytest.raises(ohs.OhsError):
+        b.broadcast_hrir(comm, 3)                        # root outside the communicator
+    comm.close()

@@ -68,6 +68,29 @@ def _worker(rank, world, port, out_dir):
         P.reduce_bus(bus, dst=0)
         if rank == 0:
             assert torch.equal(bus, torch.full((2, 1000), float(sum(range(1, world + 1)))))
+        # partition counts travel with the table: the source derives them per set from its impulse responses,
+        # every receiver marks its sets with what it received — and refuses a zero
+        class FakeEngine:
+            def __init__(self, parts):
+                self.parts, self.marked = parts, {}
+
+            def num_partitions(self, path, hrir_set):
+                return self.parts[hrir_set][path]
+
+            def mark_filters_external(self, hrir_set, partitions):
+                self.marked[hrir_set] = partitions
+
+        eng = FakeEngine({0: [4, 4, 3, 1], 1: [1, 1, 1, 1], 2: [47, 47, 47, 47]} if rank == 0 else {0: [1] * 4, 1: [1] * 4, 2: [1] * 4})
+        counts = torch.tensor(P.set_partition_counts(eng, [0, 1, 2]) if rank == 0 else [0, 0, 0], dtype=torch.int32)
+        P.broadcast_table(counts, src=0)
+        P.apply_received_partition_counts(eng, [0, 1, 2], counts.tolist(), is_src=(rank == 0))
+        assert eng.marked == ({} if rank == 0 else {0: 4, 1: 1, 2: 47})
+        if rank != 0:
+            try:
+                P.apply_received_partition_counts(eng, [0], [0], is_src=False)
+                raise AssertionError("a zero partition count must be refused")
+            except RuntimeError:
+                pass
         np.save(os.path.join(out_dir, "ok_%d.npy" % rank), np.array([1]))
     finally:
         dist.destroy_process_group()
