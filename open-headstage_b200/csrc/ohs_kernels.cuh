@@ -51,7 +51,10 @@ constexpr int kEqSkew = 4;     // steps between neighbouring lanes of the systol
                                // kernel 4 wins (948 k vs 908 k stream-s/s: fewer live registers, shorter fill and drain)
 constexpr int kEqCoefStride = 8;  // floats per (eq_set, band): b0 b1 b2 a1 a2 enabled pad pad
 
-enum NamedBarrier { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarEq = 5, kBarConv = 6, kBarStream0 = 7 };
+// kBarStream0 + g (g < 7) synchronises the threads of one stream's transform when they span several warps;
+// kBarInitConv / kBarInitEq: the staging warp has initialised the mbarriers (it arrives, the other role waits)
+enum NamedBarrier { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarEq = 5, kBarConv = 6, kBarStream0 = 7,
+                    kBarInitConv = 14, kBarInitEq = 15 };
 
 struct RenderParams {
     const float* in;            // [stream][2][row_stride]
@@ -532,7 +535,7 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
         const float* st = reinterpret_cast<const float*>(p.eqs + (size_t)s * kMaxBands + band_b);
         bs1 = st[ch]; bs2 = st[2 + ch];
     }
-    __syncthreads();   // the CTA's one common barrier: the staging warp has initialised the mbarriers
+    bar_sync(kBarInitEq, 32 + SM::kEqThreads);   // the staging warp has initialised the mbarriers
 
     OHS_STAMP_IF(threadIdx.x == 0, p, 2);
     // Input rows: block t sits in stage buffer t % 3 once that buffer's mbarrier has completed its (t/3)-th phase.
@@ -772,6 +775,9 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     OHS_STAMP_IF(threadIdx.x == 0, p, 8);
 }
 
+// block 0 of a launch arrives by TMA unless it is a ragged (EQ-only) last block, which the EQ warps load themselves
+__device__ __forceinline__ bool first_block_by_tma(const RenderParams& p, int B) { return p.n_blocks > 1 || p.tail_frames == B; }
+
 // ---------------------------------------------------------------------------------------------------------------
 // staging warp
 // ---------------------------------------------------------------------------------------------------------------
@@ -797,13 +803,17 @@ __device__ __forceinline__ void stager_warp_main(const RenderParams& p, unsigned
             tma_load_1d(dst_base + (row >> 1) * SM::kStageStride + (row & 1) * SM::kRowR, src, (unsigned)(B * sizeof(float)), full);
         }
     };
-    // The CTA's prologue data also arrives by TMA, all of it in flight at once and none of it through registers: the
-    // twiddle tables and the shared filter spectra (constant across this handle's launches: issued BEFORE the wait for
-    // the previous launch), then block 0's input rows (the EQ warps start the moment they land), the overlap-save
-    // history rows of the CTA's streams into ring slot 2, and the next two blocks' rows.  Only the convolution warps wait
-    // for the prologue barrier.  Nothing has touched these buffers through the generic proxy yet: no proxy fence.
+    // The CTA's prologue data also arrives by TMA, all of it in flight at once and none of it through registers.  A TMA
+    // copy is a warp-uniform instruction: a warp that issues one copy per lane issues them one after the other (~70
+    // cycles each), so the copies a launch's first block waits for are spread over the warps: this warp initialises
+    // the mbarriers and brings in the twiddle tables and the shared filter spectra (constant across this handle's
+    // launches: issued BEFORE the wait for the previous launch); each stream's convolution warp fetches that stream's
+    // block-0 input rows and overlap-save history rows (conv_warps_main); blocks 1 and 2 follow from here.
     {
         uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
+        const unsigned tw_bytes = (unsigned)(sizeof(float2) * N);
+        const unsigned filt_bytes = (unsigned)(p.filt_in_smem * N * sizeof(float4));
+        const unsigned hist_bytes = p.conv_enable ? (unsigned)(n_str * 2 * B * sizeof(float)) : 0u;
         if (row == 0) {
             mbar_init(&bars[0], 1);   // stage_full[0..2]: input rows of block t in stage buffer t % 3
             mbar_init(&bars[1], 1);
@@ -812,35 +822,26 @@ __device__ __forceinline__ void stager_warp_main(const RenderParams& p, unsigned
             mbar_init(&bars[4], 1);
             mbar_init(&bars[5], 1);   // prologue_full: twiddles, shared filter spectra, overlap-save history
             fence_mbar_init();
+            // the byte counts the other warps' copies will complete (block 0's rows, the history rows)
+            if (first_block_by_tma(p, B)) mbar_expect_tx(&bars[0], (unsigned)(n_str * 2 * B * sizeof(float)));
+            mbar_expect_tx(&bars[5], tw_bytes + filt_bytes + hist_bytes);
         }
         __syncwarp();
+        bar_arrive(kBarInitConv, 32 + G * SM::T);
+        bar_arrive(kBarInitEq, 32 + SM::kEqThreads);
         OHS_STAMP_IF(row == 0, p, 10);
-        uint64_t* pro = bars + 5;
-        const unsigned tw_bytes = (unsigned)(sizeof(float2) * N);
-        const unsigned filt_bytes = (unsigned)(p.filt_in_smem * N * sizeof(float4));
-        const unsigned hist_bytes = p.conv_enable ? (unsigned)(n_str * 2 * B * sizeof(float)) : 0u;
         if (row == 0) {
-            mbar_expect_tx(pro, tw_bytes + filt_bytes + hist_bytes);
-            tma_load_1d(smem + SM::kTwOff, p.tw, tw_bytes, pro);
+            tma_load_1d(smem + SM::kTwOff, p.tw, tw_bytes, &bars[5]);
             // the fused single-partition path reads bin k at position k: its table lands in stream 0's (idle) FFT buffers
             // and the convolution warps permute it into place; every other path keeps the global even-bins-first layout
-            if (filt_bytes) tma_load_1d(smem + (SM::kFusedMac && p.filt_in_smem == 1 ? SM::kZOff : SM::kFiltOff), p.filt, filt_bytes, pro);
+            if (filt_bytes) tma_load_1d(smem + (SM::kFusedMac && p.filt_in_smem == 1 ? SM::kZOff : SM::kFiltOff), p.filt, filt_bytes, &bars[5]);
         }
         OHS_STAMP_IF(row == 0, p, 11);
         grid_dependency_wait();
         OHS_STAMP_IF(row == 0, p, 12);
-        issue(0, false);
-        OHS_STAMP_IF(row == 0, p, 13);
-        if (hist_bytes && row < 2 * n_str) {
-            float* ring = reinterpret_cast<float*>(smem + SM::kRingOff);
-            tma_load_1d(ring + (row >> 1) * SM::kRingStride + 2 * SM::kRingSlot + (row & 1) * SM::kRingRowR,
-                        reinterpret_cast<const float*>(p.prev) + ((size_t)(stream0 + (row >> 1)) * 2 + (row & 1)) * B,
-                        (unsigned)(B * sizeof(float)), pro);
-        }
     }
     issue(1, false); issue(2, false);
     OHS_STAMP_IF(row == 0, p, 9);
-    __syncthreads();   // the CTA's one common barrier: the mbarriers exist for everybody else
     for (int t = 0; t < p.n_blocks; ++t) {   // every block: the barriers count this warp
         bar_sync(kBarFull0 + (t & 1), SM::kFullCount);
         issue(t + 3, true);
@@ -922,10 +923,22 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     float* out_l = p.out + ((size_t)(s - p.io_first_stream) * 2) * p.row_stride;
     float* out_r = out_l + p.row_stride;
     auto stream_sync = [&]() { if (T > 32) bar_sync(kBarStream0 + g, T); else __syncwarp(); };
-    // the delay line and the history rows are what the previous launch wrote
+    // the delay line, the history rows and possibly the input rows are what the previous launch wrote
     grid_dependency_wait();
-    __syncthreads();   // the CTA's one common barrier: the staging warp has initialised the mbarriers
-    // twiddles, shared filter spectra and history rows, brought in by the staging warp's TMA copies
+    bar_sync(kBarInitConv, 32 + G * T);   // the staging warp has initialised the mbarriers
+    // this stream's block-0 input rows and overlap-save history rows (ring slot 2): two copies each, issued here so
+    // that the CTA's streams fetch theirs side by side (stager_warp_main)
+    if (valid && tid < 2) {
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
+        if (first_block_by_tma(p, B))
+            tma_load_1d(reinterpret_cast<float*>(smem + SM::kStageOff) + g * SM::kStageStride + tid * SM::kRowR,
+                        p.in + ((size_t)(s - p.io_first_stream) * 2 + tid) * p.row_stride, (unsigned)(B * sizeof(float)), &bars[0]);
+        if (p.conv_enable)
+            tma_load_1d(ring_g + 2 * SM::kRingSlot + tid * SM::kRingRowR, reinterpret_cast<const float*>(p.prev) + ((size_t)s * 2 + tid) * B,
+                        (unsigned)(B * sizeof(float)), &bars[5]);
+    }
+    OHS_STAMP_IF(ft == 0, p, 13);
+    // twiddles, shared filter spectra and history rows have landed
     mbar_wait(reinterpret_cast<uint64_t*>(smem + SM::kMbarOff) + 5, 0u);
     OHS_STAMP_IF(ft == 0, p, 1);
     if constexpr (SM::kFusedMac && SM::kFiltSmemBytes > 0) {
@@ -1227,16 +1240,15 @@ __global__ void __maxnreg__((RenderSmem<N, G, V>::kMaxRegs)) render_kernel(const
     const int stream0 = p.first_stream + blockIdx.x * G;
     OHS_STAMP(p, 0);
     launch_dependents();   // the next launch's CTAs may take this SM as soon as this CTA leaves it
-    // No common prologue: every role runs its own state-independent set-up first (the staging warp initialises the
-    // mbarriers and starts the TMA copies, the EQ warps fetch their coefficients), waits (griddepcontrol) for the
-    // previous launch only where it first touches what that launch wrote, and then meets the others at the CTA's single
-    // __syncthreads.
+    // No common prologue and no CTA-wide barrier: every role runs its own state-independent set-up first (the staging
+    // warp initialises the mbarriers and starts the TMA copies of the constant tables, the EQ warps fetch their
+    // coefficients), waits (griddepcontrol) for the previous launch only where it first touches what that launch wrote,
+    // and the EQ and convolution warps wait on a named barrier for the staging warp's mbarrier initialisation.
     const int warp = threadIdx.x >> 5;
     if (warp < SM::kEqWarps) { eq_warp_main<N, G, V>(p, smem, stream0, warp); return; }
     if (warp == SM::kStagerWarpId) { stager_warp_main<N, G, V>(p, smem, stream0); return; }
     const int conv_index = find_conv_index<N, G, V>(warp, std::make_integer_sequence<int, SM::kConvWarps>{});
-    if (conv_index >= 0) { conv_warps_main<N, G, V>(p, smem, stream0, conv_index); return; }
-    __syncthreads();   // placement padding: take part in the common barrier, then leave
+    if (conv_index >= 0) conv_warps_main<N, G, V>(p, smem, stream0, conv_index);  // other warp slots are placement padding
 }
 
 }  // namespace ohs

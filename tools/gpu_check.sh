@@ -8,7 +8,7 @@ if [ -f open-headstage_b200/libohs_cuda_trace.so ]; then
 fi
 for a in "2 1 64" "2 2 32" "2 4 16" "3 1 32" "5 1 16"; do timeout 120 python tools/trace_k1.py $a >> $T 2>>gpurun_out/${tag}_trace.err; done
 cat $T; tail -3 gpurun_out/${tag}_trace.err
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-configs > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 python - <<PY
 import json
 try:

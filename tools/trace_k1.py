@@ -22,7 +22,7 @@ c = S.CONFIGS[cfg]
 n_streams, block, taps, fs = c["n_streams"], c["block"], c["taps"], c["fs"]
 NAMES = ["entry", "prologue done", "eq: coeffs loaded", "eq: first rows landed", "eq: last block filtered", "conv: first block ready",
          "conv: last block written", "conv: history saved", "eq: state saved", "stager: first copies issued", "stager: mbarriers initialised",
-         "stager: constant tables issued", "stager: previous launch complete", "stager: block 0 rows issued"]
+         "stager: constant tables issued", "stager: previous launch complete", "conv: block 0 and history rows issued"]
 
 
 def run(pdl: str):
