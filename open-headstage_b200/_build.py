@@ -93,6 +93,7 @@ def build_library(force: bool = False, verbose: bool = False, out: str | None = 
 
 
 HOST_TEST_BIN = os.path.join(HERE, "host", "ref_unit_tests")
+HOST_INPUTS_BIN = os.path.join(HERE, "host", "host_inputs_tool")
 
 
 def build_host_tests(force: bool = False) -> str:
@@ -104,3 +105,15 @@ def build_host_tests(force: bool = False) -> str:
         cmd = ["g++", "-O2", "-std=c++17", "-o", HOST_TEST_BIN, src, "-L" + HERE, "-lohs_cuda", "-Wl,-rpath,$ORIGIN/.."]
         subprocess.check_call(cmd, cwd=ROOT)
     return HOST_TEST_BIN
+
+
+def build_host_inputs_tool(force: bool = False) -> str:
+    """g++ build of host/host_inputs_tool.cpp: the C++ SOFA reader (zlib) and AutoEQ parser next to the hot path, plus a
+    render mode that drives them into the engine through the C++ mirror objects."""
+    src = os.path.join(HERE, "host", "host_inputs_tool.cpp")
+    deps = [src] + [os.path.join(HERE, "host", f) for f in ("dsp.hpp", "sofa.hpp", "autoeq.hpp")] + [os.path.join(ROOT, "include", "ohs.h")]
+    if force or not os.path.exists(HOST_INPUTS_BIN) or any(os.path.getmtime(d) > os.path.getmtime(HOST_INPUTS_BIN) for d in deps):
+        build_library()
+        cmd = ["g++", "-O2", "-std=c++17", "-o", HOST_INPUTS_BIN, src, "-L" + HERE, "-lohs_cuda", "-lz", "-Wl,-rpath,$ORIGIN/.."]
+        subprocess.check_call(cmd, cwd=ROOT)
+    return HOST_INPUTS_BIN
