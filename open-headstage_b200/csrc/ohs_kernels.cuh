@@ -42,8 +42,12 @@ constexpr int kMaxBands = 10;
 // RenderSmem::kEqBpl.  For config 2's seven streams per CTA two bands per lane is the one that fits: with one band per
 // lane (five EQ warps) two EQ warps share a scheduler partition and the block time is the same (844 k vs 852 k
 // stream-s/s) for more issue slots.
+// Placement weight of an EQ warp in units of a convolution warp (RenderSmem::place).  Round 2 re-measurement on config 2
+// (profiles/r02_ab_placement.txt): weight 3 -> (1, 1, 1, 4) convolution warps next to the three EQ warps, 16 warp
+// slots, 128 registers per thread, no spills: 1.081 M stream-s/s; weight 4 -> (0, 1, 1, 5), 20 warp slots, 96
+// registers, 360 bytes of spills in the convolution warps: 1.003 M; weight 5: 0.920 M.
 #ifndef OHS_EQ_WEIGHT
-#define OHS_EQ_WEIGHT 4
+#define OHS_EQ_WEIGHT 3
 #endif
 constexpr int kMaxG = 7;       // streams per CTA
 constexpr int kEqSkew = 4;     // steps between neighbouring lanes of the systolic chain: a shuffled value is consumed 3 steps
@@ -448,7 +452,12 @@ template <int N, int G, int V = 0> struct RenderSmem {
     static constexpr int kMinBlocks0 = kBySmem < kByRegs ? kBySmem : kByRegs;
     static constexpr int kMinBlocks = kMinBlocks0 < 1 ? 1 : (kMinBlocks0 > 4 ? 4 : kMinBlocks0);
     static constexpr int kMaxRegs0 = (65536 / (kMinBlocks * 32 * kWarpsAlloc)) / 8 * 8;
-    static constexpr int kMaxRegs = kMaxRegs0 > 168 ? 168 : (kMaxRegs0 < 32 ? 32 : kMaxRegs0);
+#ifdef OHS_REG_CAP   // A/B experiments only (tools/ab_build.py): a lower register cap changes ptxas's schedule of the EQ loop
+    static constexpr int kMaxRegs1 = kMaxRegs0 > OHS_REG_CAP ? OHS_REG_CAP : kMaxRegs0;
+#else
+    static constexpr int kMaxRegs1 = kMaxRegs0;
+#endif
+    static constexpr int kMaxRegs = kMaxRegs1 > 168 ? 168 : (kMaxRegs1 < 32 ? 32 : kMaxRegs1);
 };
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -107,10 +107,12 @@ class ObjectMixer:
     applied ONCE to the reduced bus there (the definition of SURVEY.md §8e — the reference has no multi-source mode).
 
     All set-up (engine, one HRIR set per stream, filter transforms, scratch) happens in the constructor; render() holds
-    only the data path: process -> mix -> reduce -> bus EQ."""
+    only the data path, pipelined over time chunks: process(c) -> mix(c) -> reduce(c) on the engine's stream while the
+    bus EQ of chunk c-1 — one strictly sequential biquad chain, the longest single dependency of this config — runs on
+    its own stream."""
 
     def __init__(self, pkg, hrirs, block: int, fs: float, n_frames: int, eq_preset=None, gain: float = 1.0, device: int = 0,
-                 dst: int = 0, group=None, comm=None):
+                 dst: int = 0, group=None, comm=None, chunk_blocks: int = 96):
         import numpy as np
 
         self.comm = comm   # create_comm(): the bus reduce is then the C ABI's ohs_reduce_bus on the engine's stream
@@ -118,6 +120,7 @@ class ObjectMixer:
         n_src, two, taps = hrirs.shape
         assert two == 2 and n_src % 2 == 0 and n_frames % block == 0 and n_frames % 4 == 0
         self.n_src, self.n_streams, self.n_frames, self.block, self.dst, self.group = n_src, n_src // 2, n_frames, block, dst, group
+        self.chunk = min(n_frames, chunk_blocks * block)
         self.device = torch.device("cuda", device)
         hrirs = np.ascontiguousarray(hrirs, dtype=np.float32)
         self.engine = eng = pkg.Engine(self.n_streams, block, taps, n_bands=0, n_hrir_sets=self.n_streams, device=device, sample_rate=fs)
@@ -127,22 +130,24 @@ class ObjectMixer:
             eng.set_ir(2, hrirs[2 * i + 1, 0], hrir_set=i)  # RSL: source 2i+1 -> left ear
             eng.set_ir(3, hrirs[2 * i + 1, 1], hrir_set=i)  # RSR: source 2i+1 -> right ear
             eng.bind_stream_hrir(i, i)
-        eng.prepare(n_frames)                                # one upload + one transform launch for all the sets
+        eng.prepare(self.chunk)                              # one upload + one transform launch for all the sets
         self.rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
         self.post = None
         if self.rank == dst and (eq_preset is not None or gain != 1.0):
-            self.post = post = pkg.Engine(1, block, 1, n_bands=10, device=device, sample_rate=fs)
+            # EQ-only engine for the bus; block 1024 selects the one-band-per-lane EQ warps (the shorter step of the two)
+            self.post = post = pkg.Engine(1, 1024, 1, n_bands=10, device=device, sample_rate=fs)
             post.set_conv_enable(False)
             if eq_preset is not None:
                 post.eq_set_preset(eq_preset)
                 post.set_eq_enable(True)
             post.set_gain(gain)
-            post.prepare(n_frames)
+            post.prepare(self.chunk)
         with torch.cuda.device(self.device):
             self.rendered = torch.empty((self.n_streams, 2, n_frames), dtype=torch.float32, device=self.device)
             self.bus = torch.zeros((2, n_frames), dtype=torch.float32, device=self.device)
             self._eng_stream = torch.cuda.ExternalStream(eng.cuda_stream(), device=self.device)
             self._post_stream = torch.cuda.ExternalStream(self.post.cuda_stream(), device=self.device) if self.post else None
+            self._red_stream = torch.cuda.Stream(self.device)   # torch.distributed's reduce runs here when no ohs_comm is given
         eng.sync()
 
     def reset(self):
@@ -157,22 +162,33 @@ class ObjectMixer:
         assert sources.is_cuda and sources.dtype == torch.float32 and sources.is_contiguous() and tuple(sources.shape) == (self.n_src, self.n_frames)
         eng = self.engine
         cur = torch.cuda.current_stream(self.device)
+        n, fsz = self.n_frames, 4
         self._eng_stream.wait_stream(cur)
-        eng.process_device(sources.data_ptr(), self.rendered.data_ptr(), self.n_frames)
-        eng.mix_device(self.rendered.data_ptr(), self.bus.data_ptr(), self.n_frames)
-        if self.comm is not None:
-            eng.reduce_bus(self.comm, self.bus.data_ptr(), self.bus.numel(), self.dst)   # NCCL, on the engine's stream
-            cur.wait_stream(self._eng_stream)
-        else:
-            cur.wait_stream(self._eng_stream)
-            reduce_bus(self.bus, dst=self.dst, group=self.group)    # NCCL, on torch's current stream
-        if self.rank != self.dst:
-            return None
-        if self.post and apply_post:
-            self._post_stream.wait_stream(cur)
-            self.post.process_device(self.bus.data_ptr(), self.bus.data_ptr(), self.n_frames)
+        red = self._red_stream
+        post_on = self.post is not None and apply_post and self.rank == self.dst
+        for c0 in range(0, n, self.chunk):
+            m = min(self.chunk, n - c0)
+            eng.process_device(sources.data_ptr() + c0 * fsz, self.rendered.data_ptr() + c0 * fsz, m, row_stride=n)
+            eng.mix_device(self.rendered.data_ptr() + c0 * fsz, self.bus.data_ptr() + c0 * fsz, m, row_stride=n, bus_stride=n)
+            if self.comm is not None:
+                for ch in range(2):   # NCCL, on the engine's stream
+                    eng.reduce_bus(self.comm, self.bus.data_ptr() + (ch * n + c0) * fsz, m, self.dst)
+                done = self._eng_stream.record_event()
+            else:
+                red.wait_stream(self._eng_stream)
+                with torch.cuda.stream(red):
+                    for ch in range(2):
+                        reduce_bus(self.bus[ch, c0:c0 + m], dst=self.dst, group=self.group)
+                done = red.record_event()
+            if post_on:
+                self._post_stream.wait_event(done)
+                self.post.process_device(self.bus.data_ptr() + c0 * fsz, self.bus.data_ptr() + c0 * fsz, m, row_stride=n)
+            else:
+                cur.wait_event(done)
+        if post_on:
             cur.wait_stream(self._post_stream)
-        return self.bus
+        cur.wait_stream(self._eng_stream)
+        return self.bus if self.rank == self.dst else None
 
 
 def render_object_mix(pkg, sources, hrirs, block: int, fs: float, eq_preset=None, gain: float = 1.0, device: int = 0,

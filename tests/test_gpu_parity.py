@@ -94,7 +94,7 @@ def test_ref_biquad_processes_when_enabled():
 # EQ: bit-exact
 # ------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("preset_name", ["typical", "harsh"])
-@pytest.mark.parametrize("n_streams,block,n_frames", [(1, 256, 4096), (7, 128, 3000), (4, 512, 5120), (3, 64, 1000)])
+@pytest.mark.parametrize("n_streams,block,n_frames", [(1, 256, 4096), (7, 128, 3000), (4, 512, 5120), (3, 64, 1000), (2, 1024, 5000), (5, 1024, 8192)])
 def test_eq_bit_exact(preset_name, n_streams, block, n_frames):
     preset = S.EQ_PRESET_TYPICAL if preset_name == "typical" else S.EQ_PRESET_HARSH
     coeffs = preset_coeffs(preset)
