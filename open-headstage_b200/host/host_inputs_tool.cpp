@@ -3,9 +3,9 @@
 //       reads the SOFA file without libmysofa/HDF5, prints M, N, the two selected indices and checksums (no GPU)
 //   host_inputs_tool autoeq <csv>
 //       prints the parsed bands (no GPU)
-//   host_inputs_tool render <file> <M> <N> <csv> <n_frames> <out.f32>
+//   host_inputs_tool render <file> <M> <N> <csv> <in.f32> <out.f32>
 //       GPU: SOFA (30 deg / 330 deg speakers) -> four set_ir calls, AutoEQ CSV -> update_band_coeffs, then the chain
-//       EQ -> convolution over a deterministic input through the C++ mirror objects; writes [2][n_frames] f32
+//       EQ -> convolution over the [2][n_frames] f32 input file through the C++ mirror objects; writes [2][n_frames] f32
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -48,14 +48,25 @@ int main(int argc, char** argv) {
         if (argc >= 8 && !std::strcmp(argv[1], "render")) {
             MySofa s = MySofa::open(argv[2], 48000.0f, (size_t)std::atol(argv[3]), (size_t)std::atol(argv[4]));
             const auto bands = parse_autoeq_csv(argv[5]);
-            const size_t n = (size_t)std::atol(argv[6]);
+            std::vector<float> l, r;
+            {
+                FILE* fi = std::fopen(argv[6], "rb");
+                if (!fi) throw std::runtime_error("cannot read input");
+                std::fseek(fi, 0, SEEK_END);
+                const size_t total = (size_t)std::ftell(fi) / sizeof(float);
+                std::fseek(fi, 0, SEEK_SET);
+                l.resize(total / 2); r.resize(total / 2);
+                if (std::fread(l.data(), sizeof(float), l.size(), fi) != l.size() || std::fread(r.data(), sizeof(float), r.size(), fi) != r.size())
+                    throw std::runtime_error("short input file");
+                std::fclose(fi);
+            }
+            const size_t n = l.size();
             ConvolutionEngine conv(512, 4096);
             const auto idx = wire_speakers(conv, s, ui_azimuth_to_sofa(-30.0f), 0.0f, ui_azimuth_to_sofa(30.0f), 0.0f, ConvolutionPath::Lsl,
                                            ConvolutionPath::Lsr, ConvolutionPath::Rsl, ConvolutionPath::Rsr);
             StereoParametricEQ eq(10, 48000.0f);
             apply_to_eq(eq, 48000.0f, bands);
-            std::vector<float> l(n), r(n), ol(n), orr(n);
-            for (size_t i = 0; i < n; ++i) { l[i] = 0.5f * std::sin(0.01f * (float)i) + ((i % 97) == 0 ? 0.25f : 0.0f); r[i] = 0.5f * std::cos(0.013f * (float)i); }
+            std::vector<float> ol(n), orr(n);
             eq.process_block(l, r);                 // Plugin::process order: EQ in place, then the convolver (src/lib.rs:1179-1200)
             conv.process_block(l, r, ol, orr);
             FILE* f = std::fopen(argv[7], "wb");
