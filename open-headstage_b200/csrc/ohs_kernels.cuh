@@ -566,8 +566,16 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
         if (SM::kEqWarps > 1) bar_sync(kBarEq, SM::kEqThreads); else __syncwarp();
     };
 
-    const int src_lane = (l == 0) ? lane : lane - CPW;
-    const bool first = (l == 0), last = (l == LPC - 1) && lane_valid;  // lanes of absent streams never store
+    // One band per lane (BPL = 1): a chain's last lane has no right neighbour, nobody reads what it shuffles.  It
+    // publishes the chain's INPUT samples there instead and the first lane takes its shuffle from it, so the choice
+    // between "input sample" and "left neighbour's output" is made on the PRODUCER side, on values that are long since in
+    // registers, and no lane executes a select on a fresh shuffle result (18 % of that loop's time went to waiting there:
+    // profiles/r01_ncu_config5_spectra_only_render.txt).  With two bands per lane the same change was measured and does
+    // not pay (config 2: 1.068 M against 1.080 M), so there the first lane keeps selecting on the consumer side.
+    constexpr bool kPubInput = (BPL == 1);
+    const int src_lane = (l == 0) ? (kPubInput ? lane + (LPC - 1) * CPW : lane) : lane - CPW;
+    const bool first = (l == 0), pub = (l == LPC - 1), last = pub && lane_valid;  // lanes of absent streams never store
+    const bool feeds = kPubInput ? pub : first;   // the lane that reads the staged input rows in the steady state
     // xsel[u]: band A's input at step u of the coming iteration, already chosen between the staged input sample (first
     // lane of a chain) and lane l-1's shuffled output.  The choice is made right behind the shuffle, an iteration ahead
     // of its use: ptxas gives a value whose only consumer lies behind the loop's back-edge the lowest priority and
@@ -605,9 +613,11 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
                 yl[u] = y;
             } else {
                 const float y = df2t_step(xsel[u], as1, as2, ab0, ab1, ab2, aa1, aa2);
-                const float r = __shfl_sync(0xffffffffu, y, src_lane);
-                if (u == 0) xsel[DL - 1] = first ? in_at(in, DL - 1) : r;
-                else xsel[u - 1] = (decltype(sel)::value && first) ? in_at(nx, u - 1) : r;
+                // producer-side select (see src_lane): the chain's last lane publishes the input sample instead of its output
+                float v = y;
+                if (u == 0) v = pub ? in_at(in, DL - 1) : y;
+                else if (decltype(sel)::value) v = pub ? in_at(nx, u - 1) : y;
+                xsel[(u + DL - 1) % DL] = __shfl_sync(0xffffffffu, v, src_lane);
                 if ((u & 3) == kStoreU && last)
                     *reinterpret_cast<float4*>(dst + (i0 + u - 3 - kOutLag)) =
                         make_float4(yl[(u + DL - 3) % DL], yl[(u + DL - 2) % DL], yl[(u + DL - 1) % DL], y);
@@ -647,9 +657,8 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
                 const bool upd_a = act_a && en_a;
                 as1 = upd_a ? t1 : as1; as2 = upd_a ? t2 : as2;
                 y = upd_a ? y : xa;
-                const float r = __shfl_sync(0xffffffffu, y, src_lane);
-                if (u == 0) xsel[DL - 1] = first ? in_at(in, DL - 1) : r;
-                else xsel[u - 1] = first ? in_at(nx, u - 1) : r;
+                const float v = pub ? (u == 0 ? in_at(in, DL - 1) : in_at(nx, u - 1)) : y;
+                xsel[(u + DL - 1) % DL] = __shfl_sync(0xffffffffu, v, src_lane);
                 if (act_a && last) dst0[na] = y;
                 yl[u] = y;
             }
@@ -670,9 +679,9 @@ __device__ __forceinline__ void eq_warp_main(const RenderParams& p, unsigned cha
     static_assert(SM::kRowR >= B + 4 && SM::kStageStride >= SM::kRowR + B + 4, "look-ahead load of the last iteration reads the pad");
     auto ld_fast = [&](In& in, const float* row, int i) {
         if constexpr (NQ == 1) {
-            if (first) in.q[0] = *reinterpret_cast<const float4*>(row + i);
+            if (feeds) in.q[0] = *reinterpret_cast<const float4*>(row + i);
         } else {
-            if (first) {
+            if (feeds) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) in.q[q] = *reinterpret_cast<const float4*>(row + i + 4 * q);
             }
