@@ -102,6 +102,15 @@ struct ohs_engine {
     float2* d_zlin = nullptr;
     float2* d_wlin = nullptr;
     size_t zlin_blocks = 0;  // blocks per sub-launch the two buffers are sized for
+    // ... and its EQ pre-pass: the EQ-filtered rows of two sub-launches (halves used alternately), written by the EQ-only
+    // kernel on its own stream while the previous chunk's transforms and products run on the engine's stream
+    float* d_xf = nullptr;   // [2 halves][stream][2][zlin_blocks * B]
+    cudaStream_t eq_stream = nullptr;
+    std::vector<cudaEvent_t> ev_eq;          // EQ pre-pass of chunk c has finished (pool, used round-robin)
+    cudaEvent_t ev_fwd[2] = {nullptr, nullptr};   // forward transforms have consumed a half of d_xf
+    cudaEvent_t ev_call = nullptr;           // everything enqueued on the engine's stream before this call
+    size_t eq_events_used = 0;
+    int tb_overlap = 1;      // OHS_TB_OVERLAP=0: EQ pre-pass on the engine's stream, one chunk per sub-launch (A/B)
 
     // FIFO adaptor (src/dsp/convolution.rs:141-182)
     std::vector<float> fifo_in, fifo_out;  // [row][cap]
@@ -115,7 +124,7 @@ using namespace ohs;
 int launch_render(ohs_engine* h, const RenderParams& p, int first_stream = 0) {
     // few blocks per launch: nothing overlaps inside the launch, so the variant built for latency runs it
     const bool latency = p.n_blocks <= h->latency_blocks && !p.spectra_only;
-    RenderLaunch L{h->G, h->cfg.device, h->stream, first_stream, latency, h->dependent_launch};
+    RenderLaunch L{h->G, h->cfg.device, h->stream, first_stream, latency ? 1 : 0, h->dependent_launch};
     RenderParams q = p;
     q.trace = h->d_trace;
     cudaError_t e = cudaErrorInvalidValue;
@@ -358,7 +367,7 @@ namespace {
 
 constexpr int kTimeBatch = 8;  // consecutive blocks a bin_conv_kernel thread accumulates (TB)
 
-template <int N> int launch_inverse(ohs_engine* h, float* d_out, int K, size_t row_stride) {
+template <int N> int launch_inverse(ohs_engine* h, const float2* d_w, float* d_out, int K, size_t row_stride) {
     constexpr size_t smem = sizeof(float2) * 2 * padded_len(N);
     static AttrOnce once;
     const int dev = h->cfg.device;
@@ -366,17 +375,42 @@ template <int N> int launch_inverse(ohs_engine* h, float* d_out, int K, size_t r
         OHS_CUDA(cudaFuncSetAttribute(inverse_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         once.mark(dev);
     }
-    inverse_kernel<N><<<dim3(K, h->cfg.n_streams), fft_threads(N), smem, h->stream>>>(h->d_wlin, d_out, h->d_tw, h->d_stream_gain, K,
+    inverse_kernel<N><<<dim3(K, h->cfg.n_streams), fft_threads(N), smem, h->stream>>>(d_w, d_out, h->d_tw, h->d_stream_gain, K,
                                                                                       (long long)row_stride);
     OHS_CUDA(cudaGetLastError());
     h->launches++;
     return OHS_OK;
 }
 
-// Long responses, many blocks per call: per sub-launch of up to `zlin_blocks` blocks, (1) delay-line history into the
-// time-ordered buffer, (2) the render kernel in spectra-only mode (EQ, forward FFT, ring and buffer writes), (3) the
-// per-bin convolution along time, (4) the inverse transforms.  The delay-line ring, the overlap-save block and the EQ
-// state end up exactly where the block-by-block path leaves them, so the two can be mixed freely between calls.
+// forward transforms of blocks [t0, t0 + k) of a sub-launch from the filtered rows xf (block 0's history: d_prev)
+template <int N> int launch_forward(ohs_engine* h, const float* xf, long long xf_stride, int t0, int k, long long zstride, int zbase, int ring_from) {
+    constexpr size_t smem = sizeof(float2) * 2 * padded_len(N);
+    static AttrOnce once;
+    const int dev = h->cfg.device;
+    if (smem > 48 * 1024 && once.need(dev)) {
+        OHS_CUDA(cudaFuncSetAttribute(forward_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        once.mark(dev);
+    }
+    forward_kernel<N><<<dim3(k, h->cfg.n_streams), fft_threads(N), smem, h->stream>>>(
+        xf, xf_stride, t0, reinterpret_cast<const float*>(h->d_prev), h->d_zlin, zstride, zbase, h->d_fdl, h->pmax, h->head, ring_from,
+        h->d_stream_hrir, h->d_set_parts, h->d_tw);
+    OHS_CUDA(cudaGetLastError());
+    h->launches++;
+    return OHS_OK;
+}
+
+// Long responses, many blocks per call.  Per sub-launch of up to `zlin_blocks` blocks:
+//   (0) EQ pre-pass: the EQ-only variant of the render kernel (a thin CTA per three streams: two EQ warps, 38 KB) filters
+//       the input rows into d_xf on its OWN stream.  The biquad chain is strictly sequential — 1024 steps per block at
+//       the chain's latency, with most of the SM idle — while everything below is throughput-bound and independent of
+//       later input, so the pre-pass of chunk c+1 runs beside the transforms and products of chunk c;
+//   (1) delay-line history into the time-ordered buffer (once per sub-launch);
+//   and per chunk (8, 8, 16, 32 blocks in a call's first sub-launch, so that only the first 8 blocks' EQ is exposed; the
+//   whole sub-launch afterwards, when the pre-pass is running ahead anyway):
+//   (2) forward transforms (spectra to the ring and to the time-ordered buffer), (3) the per-bin convolution along time,
+//   (4) the inverse transforms.
+// The delay-line ring, the overlap-save block and the EQ state end up exactly where the block-by-block path leaves
+// them, so the two can be mixed freely between calls.
 // whether a call of n_blocks takes the time-batched route
 bool time_batch_eligible(const ohs_engine* h, int n_blocks) {
     return h->time_batch && h->conv_enable && h->pmax >= 8 && n_blocks >= kTimeBatch && h->cfg.n_streams <= 65535;  // (grid.y = stream)
@@ -387,72 +421,190 @@ bool time_batch_eligible(const ohs_engine* h, int n_blocks) {
 int ensure_time_batch_scratch(ohs_engine* h, int n_blocks) {
     const size_t S = (size_t)h->cfg.n_streams, N = (size_t)h->N, hist = (size_t)h->pmax - 1;
     const size_t budget = (size_t)2 << 30;
-    const size_t per_block = 2 * S * N * sizeof(float2), fixed = S * hist * N * sizeof(float2);
+    // per block: a spectrum and a product (8N bytes each) and the filtered rows in both halves of d_xf (2 * 2 * 4B = 8N)
+    const size_t per_block = 3 * S * N * sizeof(float2), fixed = S * hist * N * sizeof(float2);
     size_t kc = fixed < budget ? (budget - fixed) / per_block : 0;
     kc = std::min<size_t>(std::min<size_t>(kc, 64), (size_t)n_blocks);
     if (kc < (size_t)kTimeBatch) return 1;
     if (kc > h->zlin_blocks) {
         OHS_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->eq_stream) OHS_CUDA(cudaStreamSynchronize(h->eq_stream));
         if (h->d_zlin) OHS_CUDA(cudaFree(h->d_zlin));
         if (h->d_wlin) OHS_CUDA(cudaFree(h->d_wlin));
-        h->d_zlin = h->d_wlin = nullptr; h->zlin_blocks = 0;
+        if (h->d_xf) OHS_CUDA(cudaFree(h->d_xf));
+        h->d_zlin = h->d_wlin = nullptr; h->d_xf = nullptr; h->zlin_blocks = 0;
         OHS_CUDA(cudaMalloc(&h->d_zlin, S * (hist + kc) * N * sizeof(float2)));
         OHS_CUDA(cudaMalloc(&h->d_wlin, S * kc * N * sizeof(float2)));
+        OHS_CUDA(cudaMalloc(&h->d_xf, 2 * S * 2 * kc * (size_t)h->B * sizeof(float)));
         h->zlin_blocks = kc;
+    }
+    if (!h->eq_stream) {
+        int lo = 0, hi = 0;
+        OHS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        OHS_CUDA(cudaStreamCreateWithPriority(&h->eq_stream, cudaStreamNonBlocking, hi));   // its thin CTAs go first
+        OHS_CUDA(cudaEventCreateWithFlags(&h->ev_fwd[0], cudaEventDisableTiming));
+        OHS_CUDA(cudaEventCreateWithFlags(&h->ev_fwd[1], cudaEventDisableTiming));
+        OHS_CUDA(cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming));
     }
     return OHS_OK;
 }
 
+// the per-bin convolution of blocks [0, k) behind time-ordered slot base `z`, products to `w` ([stream][k][N])
+int launch_bin_conv(ohs_engine* h, const float2* z, float2* w, int k, long long zstride) {
+    const size_t S = (size_t)h->cfg.n_streams, N = (size_t)h->N;
+    const dim3 blk(128);
+    const unsigned gx = (unsigned)((N / 2 + 31) / 32), gz = (unsigned)((S + 3) / 4);
+    static AttrOnce once;
+    const int dev = h->cfg.device;
+    if (once.need(dev)) {
+        OHS_CUDA(cudaFuncSetAttribute(bin_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 16 * 128 * sizeof(float4))));
+        once.mark(dev);
+    }
+    // 16 blocks per thread (half the spectrum and filter traffic per FMA) from 16 blocks per launch on: measured faster
+    // than 8 at K = 16 (0.529 vs 0.560 ms), 32, 64 and 128 on config 5
+    if (k >= 16)
+        bin_conv_kernel<16><<<dim3(gx, (unsigned)((k + 15) / 16), gz), blk, 2 * 16 * 128 * sizeof(float4), h->stream>>>(
+            z, w, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride);
+    else
+        bin_conv_kernel<kTimeBatch><<<dim3(gx, (unsigned)((k + kTimeBatch - 1) / kTimeBatch), gz), blk, 2 * kTimeBatch * 128 * sizeof(float4), h->stream>>>(
+            z, w, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride);
+    OHS_CUDA(cudaGetLastError());
+    h->launches++;
+    return OHS_OK;
+}
+
+// EQ pre-pass of `frames` frames of every stream on `stream`: rows in (stride in_stride) -> rows out (stride out_stride)
+int launch_eq_prepass(ohs_engine* h, const RenderParams& base, const float* d_in, long long in_stride, float* d_out, long long out_stride,
+                      size_t frames, cudaStream_t stream) {
+    constexpr int kB = 256;   // the EQ-only variant exists for N = 512; the chain does not care how its rows are cut into blocks
+    RenderParams q = base;
+    q.in = d_in; q.out = d_out; q.row_stride = in_stride; q.out_row_stride = out_stride;
+    q.n_blocks = (int)((frames + kB - 1) / kB);
+    q.tail_frames = (int)(frames - (size_t)(q.n_blocks - 1) * kB);
+    q.conv_enable = 0; q.eq_enable = 1; q.spectra_only = 0; q.zlin = nullptr; q.filt_in_smem = 0;
+    q.trace = nullptr;
+    RenderLaunch L{3, h->cfg.device, stream, 0, 2, h->dependent_launch};
+    const cudaError_t e = render_launch_512(L, q);
+    if (e != cudaSuccess) return fail(OHS_ERR_CUDA, "EQ pre-pass launch failed: %s", cudaGetErrorString(e));
+    h->launches++;
+    return OHS_OK;
+}
+
 int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float* d_out, size_t row_stride) {
-    const size_t S = (size_t)h->cfg.n_streams, N = (size_t)h->N, hist = (size_t)h->pmax - 1;
+    const size_t S = (size_t)h->cfg.n_streams, N = (size_t)h->N, hist = (size_t)h->pmax - 1, B = (size_t)h->B;
     {
         const int rc = ensure_time_batch_scratch(h, p.n_blocks);
         if (rc) return rc;   // 1: caller falls back to the block-by-block kernel
     }
-    const long long zstride = (long long)((hist + h->zlin_blocks) * N);
+    const size_t kc = h->zlin_blocks;
+    const long long zstride = (long long)((hist + kc) * N);
+    const long long xstride = (long long)(kc * B);               // frames between the rows of a half of d_xf
+    const size_t xhalf = S * 2 * kc * B;                         // floats per half
     const int total = p.n_blocks;
-    for (int done = 0; done < total;) {
-        const int k = std::min<int>((int)h->zlin_blocks, total - done);
+    const bool eq_on = p.eq_enable != 0;
+    const bool overlap = eq_on && h->tb_overlap;
+    cudaStream_t eqs = overlap ? h->eq_stream : h->stream;
+    const int n_sub = (total + (int)kc - 1) / (int)kc;
+    // chunks of sub-launch j: (first block inside the sub-launch, blocks)
+    auto chunks_of = [&](int j, std::vector<std::pair<int, int>>& out) {
+        out.clear();
+        const int k = std::min<int>((int)kc, total - j * (int)kc);
+        if (!overlap || j > 0 || k < 24) { out.emplace_back(0, k); return; }
+        int at = 0;
+        for (int c : {8, 8, 16, 32}) {
+            if (k - at < 2 * c && k - at >= 8) { out.emplace_back(at, k - at); at = k; break; }
+            out.emplace_back(at, c); at += c;
+            if (at >= k) break;
+        }
+        if (at < k) out.emplace_back(at, k - at);
+    };
+    std::vector<std::vector<std::pair<int, int>>> chunks(n_sub);
+    std::vector<std::vector<cudaEvent_t>> done_ev(n_sub);
+    for (int j = 0; j < n_sub; ++j) chunks_of(j, chunks[j]);
+    auto next_event = [&](cudaEvent_t* ev) -> int {
+        if (h->eq_events_used == h->ev_eq.size()) {
+            cudaEvent_t e;
+            OHS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->ev_eq.push_back(e);
+        }
+        *ev = h->ev_eq[h->eq_events_used++];
+        return OHS_OK;
+    };
+    h->eq_events_used = 0;
+    // enqueue the EQ pre-pass of sub-launch j (its chunks back to back on the EQ stream, an event behind each)
+    auto enqueue_eq = [&](int j) -> int {
+        if (!eq_on) return OHS_OK;
+        float* xf = h->d_xf + (size_t)(j & 1) * xhalf;
+        if (overlap && j >= 2) OHS_CUDA(cudaStreamWaitEvent(eqs, h->ev_fwd[j & 1], 0));   // sub-launch j-2's transforms have read this half
+        for (const auto& c : chunks[j]) {
+            const size_t f0 = ((size_t)j * kc + c.first) * B;
+            int rc = launch_eq_prepass(h, p, d_in + f0, (long long)row_stride, xf + (size_t)c.first * B, xstride, (size_t)c.second * B, eqs);
+            if (rc) return rc;
+            if (overlap) {
+                cudaEvent_t ev;
+                rc = next_event(&ev);
+                if (rc) return rc;
+                OHS_CUDA(cudaEventRecord(ev, eqs));
+                done_ev[j].push_back(ev);
+            }
+        }
+        return OHS_OK;
+    };
+    if (overlap) {
+        // the EQ stream starts behind everything already enqueued on the engine's stream (EQ state, input rows)
+        OHS_CUDA(cudaEventRecord(h->ev_call, h->stream));
+        OHS_CUDA(cudaStreamWaitEvent(eqs, h->ev_call, 0));
+        for (int j = 0; j < std::min(2, n_sub); ++j) { const int rc = enqueue_eq(j); if (rc) return rc; }
+    }
+    for (int j = 0; j < n_sub; ++j) {
+        const int k = std::min<int>((int)kc, total - j * (int)kc);
+        if (!overlap) { const int rc = enqueue_eq(j); if (rc) return rc; }
         gather_history_kernel<<<dim3((unsigned)hist, (unsigned)S), 256, 0, h->stream>>>(h->d_fdl, h->d_zlin, (int)N, h->pmax, h->head, zstride);
         OHS_CUDA(cudaGetLastError());
         h->launches++;
-        p.in = d_in + (size_t)done * h->B; p.out = d_out + (size_t)done * h->B;
-        p.n_blocks = k; p.tail_frames = h->B; p.head = h->head;
-        p.zlin = h->d_zlin; p.zlin_stride = zstride; p.zlin_base = (int)hist; p.spectra_only = 1;
-        int rc = launch_render(h, p);
-        if (rc) return rc;
-        {
-            const dim3 blk(128);
-            const unsigned gx = (unsigned)((N / 2 + 31) / 32), gz = (unsigned)((S + 3) / 4);
-            static AttrOnce once;
-            const int dev = h->cfg.device;
-            if (once.need(dev)) {
-                OHS_CUDA(cudaFuncSetAttribute(bin_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 16 * 128 * sizeof(float4))));
-                once.mark(dev);
+        // filtered rows of this sub-launch: a half of d_xf (with the EQ off, a copy of the input rows: the transforms read
+        // a block's predecessor too, which an in-place call has overwritten with output by then)
+        const float* xf = h->d_xf + (size_t)(j & 1) * xhalf;
+        const long long xs = xstride;
+        if (!eq_on)
+            OHS_CUDA(cudaMemcpy2DAsync(h->d_xf + (size_t)(j & 1) * xhalf, (size_t)xstride * sizeof(float), d_in + (size_t)j * kc * B,
+                                       row_stride * sizeof(float), (size_t)k * B * sizeof(float), S * 2, cudaMemcpyDeviceToDevice, h->stream));
+        float* out_j = d_out + (size_t)j * kc * B;
+        for (size_t ci = 0; ci < chunks[j].size(); ++ci) {
+            const int c0 = chunks[j][ci].first, ck = chunks[j][ci].second;
+            if (overlap) OHS_CUDA(cudaStreamWaitEvent(h->stream, done_ev[j][ci], 0));
+            int rc;
+            switch (h->N) {
+                case 128: rc = launch_forward<128>(h, xf, xs, c0, ck, zstride, (int)hist, k - h->pmax); break;
+                case 256: rc = launch_forward<256>(h, xf, xs, c0, ck, zstride, (int)hist, k - h->pmax); break;
+                case 512: rc = launch_forward<512>(h, xf, xs, c0, ck, zstride, (int)hist, k - h->pmax); break;
+                case 1024: rc = launch_forward<1024>(h, xf, xs, c0, ck, zstride, (int)hist, k - h->pmax); break;
+                case 2048: rc = launch_forward<2048>(h, xf, xs, c0, ck, zstride, (int)hist, k - h->pmax); break;
+                default: rc = fail(OHS_ERR_INVALID, "unsupported transform size %d", h->N);
             }
-            // 16 blocks per thread (half the spectrum and filter traffic per FMA) from 16 blocks per sub-launch on:
-            // measured faster than 8 at K = 16 (0.529 vs 0.560 ms), 32, 64 and 128 on config 5
-            const bool tb16 = k >= 16;
-            if (tb16)
-                bin_conv_kernel<16><<<dim3(gx, (unsigned)((k + 15) / 16), gz), blk, 2 * 16 * 128 * sizeof(float4), h->stream>>>(
-                    h->d_zlin, h->d_wlin, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride);
-            else
-                bin_conv_kernel<kTimeBatch><<<dim3(gx, (unsigned)((k + kTimeBatch - 1) / kTimeBatch), gz), blk, 2 * kTimeBatch * 128 * sizeof(float4), h->stream>>>(
-                    h->d_zlin, h->d_wlin, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride);
+            if (rc) return rc;
+            float2* w = h->d_wlin + S * (size_t)c0 * N;
+            rc = launch_bin_conv(h, h->d_zlin + (size_t)c0 * N, w, ck, zstride);
+            if (rc) return rc;
+            float* out_c = out_j + (size_t)c0 * B;
+            switch (h->N) {
+                case 128: rc = launch_inverse<128>(h, w, out_c, ck, row_stride); break;
+                case 256: rc = launch_inverse<256>(h, w, out_c, ck, row_stride); break;
+                case 512: rc = launch_inverse<512>(h, w, out_c, ck, row_stride); break;
+                case 1024: rc = launch_inverse<1024>(h, w, out_c, ck, row_stride); break;
+                case 2048: rc = launch_inverse<2048>(h, w, out_c, ck, row_stride); break;
+                default: rc = fail(OHS_ERR_INVALID, "unsupported transform size %d", h->N);
+            }
+            if (rc) return rc;
         }
-        OHS_CUDA(cudaGetLastError());
-        h->launches++;
-        switch (h->N) {
-            case 128: rc = launch_inverse<128>(h, p.out, k, row_stride); break;
-            case 256: rc = launch_inverse<256>(h, p.out, k, row_stride); break;
-            case 512: rc = launch_inverse<512>(h, p.out, k, row_stride); break;
-            case 1024: rc = launch_inverse<1024>(h, p.out, k, row_stride); break;
-            case 2048: rc = launch_inverse<2048>(h, p.out, k, row_stride); break;
-            default: rc = fail(OHS_ERR_INVALID, "unsupported transform size %d", h->N);
+        // overlap-save history of the next sub-launch or call: this one's last filtered block
+        OHS_CUDA(cudaMemcpy2DAsync(h->d_prev, B * sizeof(float), xf + (size_t)(k - 1) * B, (size_t)xs * sizeof(float), B * sizeof(float),
+                                   S * 2, cudaMemcpyDeviceToDevice, h->stream));
+        if (overlap) {
+            OHS_CUDA(cudaEventRecord(h->ev_fwd[j & 1], h->stream));
+            if (j + 2 < n_sub) { const int rc = enqueue_eq(j + 2); if (rc) return rc; }
         }
-        if (rc) return rc;
         h->head = (int)(((size_t)h->head + k) % (size_t)h->pmax);
-        done += k;
     }
     return OHS_OK;
 }
@@ -493,6 +645,7 @@ int ohs_create(const ohs_config* cfg, ohs_engine** out) {
     h->pmax = (cfg->max_taps + B - 1) / B;
     h->G = pick_streams_per_cta(h);
     if (const char* e = getenv("OHS_TIME_BATCH")) h->time_batch = atoi(e) != 0;
+    if (const char* e = getenv("OHS_TB_OVERLAP")) h->tb_overlap = atoi(e) != 0;
     if (const char* e = getenv("OHS_STAGE_MB")) { const long mb = atol(e); if (mb >= 1 && mb <= 4096) h->stage_bytes = (size_t)mb << 20; }
     if (const char* e = getenv("OHS_PDL")) h->dependent_launch = atoi(e) != 0;
     if (const char* e = getenv("OHS_LATENCY_BLOCKS")) h->latency_blocks = atoi(e);
@@ -579,9 +732,12 @@ int ohs_destroy(ohs_engine* h) {
     if (!h) return OHS_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->eq_stream) { cudaStreamSynchronize(h->eq_stream); cudaStreamDestroy(h->eq_stream); }
+    for (cudaEvent_t e : h->ev_eq) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->ev_fwd[0], h->ev_fwd[1], h->ev_call}) if (e) cudaEventDestroy(e);
     void* ptrs[] = {h->d_stream_hrir, h->d_stream_eq, h->d_stream_gain, h->d_filt, h->d_set_parts, h->d_set_list, h->d_set_flags,
                     h->d_fdl, h->d_prev, h->d_eqc, h->d_eqs, h->d_tw, h->d_ir, h->d_stage[0], h->d_stage[1], h->d_stage[2],
-                    h->d_zlin, h->d_wlin};
+                    h->d_zlin, h->d_wlin, h->d_xf};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < kPipe; ++i) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
@@ -806,7 +962,7 @@ int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_
     rc = commit_filters(h);
     if (rc) return rc;
     RenderParams p{};
-    p.in = d_in; p.out = d_out; p.row_stride = (long long)row_stride;
+    p.in = d_in; p.out = d_out; p.row_stride = p.out_row_stride = (long long)row_stride;
     p.n_blocks = (int)((n_frames + h->B - 1) / h->B);
     p.tail_frames = (int)(n_frames - (size_t)(p.n_blocks - 1) * h->B);
     p.n_streams = h->cfg.n_streams;

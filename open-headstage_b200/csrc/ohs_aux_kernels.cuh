@@ -165,6 +165,56 @@ __global__ void __launch_bounds__(128, 3) bin_conv_kernel(const float2* __restri
         if (t0 + tb < K) { w[(size_t)(t0 + tb) * N + k0] = a0[tb]; w[(size_t)(t0 + tb) * N + k1] = a1[tb]; }
 }
 
+// first-pass loader of the forward transform from global memory: the overlap-save window [previous block | current block]
+// of a stream's EQ-filtered rows, z = left + i*right
+struct RowWindow {
+    const float* pl; const float* pr; const float* cl; const float* cr; int B;   // cl/cr already offset by -B
+    __device__ __forceinline__ float2 ld(int i) const { return i < B ? make_float2(pl[i], pr[i]) : make_float2(cl[i], cr[i]); }
+    __device__ __forceinline__ void ld2(int i, float2& a, float2& b) const {  // i even: samples i and i+1
+        const float2 l = *reinterpret_cast<const float2*>((i < B ? pl : cl) + i), r = *reinterpret_cast<const float2*>((i < B ? pr : cr) + i);
+        a = make_float2(l.x, r.x); b = make_float2(l.y, r.y);
+    }
+};
+
+// last-pass store of the forward transform: the packed spectrum goes to the time-ordered buffer and (streams that keep
+// a delay line) to the ring slot, straight from registers
+struct SpectrumStore {
+    float2* zl; float2* zr;   // zr may be null
+    __device__ __forceinline__ void st(int i, float2 v) const { zl[i] = v; if (zr) zr[i] = v; }
+    __device__ __forceinline__ void st2(int i, float2 a, float2 b) const {
+        const float4 v = make_float4(a.x, a.y, b.x, b.y);
+        *reinterpret_cast<float4*>(zl + i) = v;
+        if (zr) *reinterpret_cast<float4*>(zr + i) = v;
+    }
+};
+
+// one CTA per (block, stream): forward transform of block t0 + blockIdx.x of the filtered rows `xf` (block 0's history is
+// the engine's overlap-save block `prev`), same plan and rounding as the render kernel's forward transform.  Only blocks
+// t >= ring_from (the sub-launch's last pmax blocks) go to the delay-line ring: the blocks of a launch run concurrently,
+// and two blocks pmax apart share a ring slot
+template <int N>
+__global__ void __launch_bounds__(SetupSmem<N>::T) forward_kernel(const float* __restrict__ xf, long long xf_stride, int t0,
+                                                                const float* __restrict__ prev, float2* __restrict__ zlin,
+                                                                long long zlin_stride, int zlin_base, float2* __restrict__ fdl,
+                                                                int pmax, int head, int ring_from, const int* __restrict__ stream_hrir,
+                                                                const int* __restrict__ set_parts, const float2* __restrict__ tw_g) {
+    constexpr int T = SetupSmem<N>::T, NP = SetupSmem<N>::NP, B = N / 2;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* b0 = reinterpret_cast<float2*>(smem);
+    float2* b1 = b0 + NP;
+    const int t = t0 + blockIdx.x, s = blockIdx.y;
+    const float* cl = xf + ((size_t)s * 2) * xf_stride + (size_t)t * B;
+    const float* cr = cl + xf_stride;
+    const float* pl = t ? cl - B : prev + (size_t)s * 2 * B;
+    const float* pr = t ? cr - B : pl + B;
+    int slot = head + t;
+    slot -= (slot / pmax) * pmax;
+    float2* zr = (t >= ring_from && set_parts[stream_hrir[s]] > 1) ? fdl + ((size_t)s * pmax + slot) * N : nullptr;
+    float2* zl = zlin + (size_t)s * zlin_stride + (size_t)(zlin_base + t) * N;
+    auto sync = [&]() { __syncthreads(); };
+    fft_run<N, T>(threadIdx.x, tw_g, b0, b1, RowWindow{pl, pr, cl - B, cr - B, B}, SpectrumStore{zl, zr}, sync, [&]() {});
+}
+
 // first-pass loader of the inverse transform from global memory, with the swap of swap o FFT o swap
 struct SpectrumSwapLoad {
     const float2* w;

@@ -63,7 +63,8 @@ enum NamedBarrier { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4
 struct RenderParams {
     const float* in;            // [stream][2][row_stride]
     float* out;
-    long long row_stride;       // frames
+    long long row_stride;       // frames between the input rows
+    long long out_row_stride;   // frames between the output rows (= row_stride except in the EQ pre-pass of the time-batched route)
     int n_blocks;               // K engine blocks this launch
     int tail_frames;            // frames in the last block: B, or fewer in EQ-only mode (conv_enable == 0)
     int n_streams;
@@ -356,7 +357,12 @@ template <int N> inline void fill_twiddles(float2* out) {
 // lone block of config 2).  One band per lane in its EQ warps was measured too and is not faster there: five EQ
 // warps put two on one scheduler partition (36 cycles per step against 34).
 template <int N, int G, int V = 0> struct RenderSmem {
-    static_assert(V == 0 || (V == 1 && N == 512), "the latency variant exists for N = 512");
+    // V = 2, N = 512: the EQ-only variant behind the time-batched route's EQ pre-pass (ohs_api.cu): the same staging and
+    // EQ warps with one band per lane, "convolution" warps that only copy the filtered rows out, no transform buffers,
+    // twiddles or filter table — a 6-warp CTA with 38 KB of shared memory (G = 3) that runs beside the route's
+    // throughput-bound kernels of the previous chunk instead of in front of them.
+    static_assert(V == 0 || ((V == 1 || V == 2) && N == 512), "the latency and EQ-only variants exist for N = 512");
+    static constexpr bool kEqOnly = (V == 2);
     static constexpr int B = N / 2;
     // convolution threads per stream (V = 0: one warp at N <= 512).  The latency variant doubles them where that keeps
     // the radix plan (N = 512: 8 points per thread, radices 8-8-8 either way), so both variants round identically.
@@ -366,7 +372,11 @@ template <int N, int G, int V = 0> struct RenderSmem {
     // warps are what the CTA can spare).  1: ten lanes per chain, three chains per warp, half the instructions and a
     // single 12-cycle dependent chain per step — for the long blocks of N >= 1024, where a CTA holds few streams and
     // the 1024-step sequential chain per block is the floor of the launch (config 5).
-    static constexpr int kEqBpl = (N >= 1024) ? 1 : 2;
+#ifdef OHS_BPL1_ALL   // A/B experiments only: one band per lane for every transform size
+    static constexpr int kEqBpl = 1;
+#else
+    static constexpr int kEqBpl = (N >= 1024 || V == 2) ? 1 : 2;
+#endif
     // lane skew of the systolic chain in steps (= steps per unrolled iteration).  One band per lane runs a step in half
     // the time, too fast for a 3-step shuffle flight: skew 8
     static constexpr int kEqSkewSteps = (B >= 128) ? (kEqBpl == 1 ? 8 : kEqSkew) : 4;
@@ -377,7 +387,7 @@ template <int N, int G, int V = 0> struct RenderSmem {
     // Single-partition responses (config 2) at N = 512: the forward transform's last pass, the spectral product and the
     // inverse transform's first pass run fused in registers (conv_warps_main).  Needs one warp per stream, equal first
     // and last radices and two butterflies of the last pass per thread.
-    static constexpr bool kFusedMac = (T == 32) && (FftPlan<N, T>::kPasses == 3) && (FftPlan<N, T>::R1 == FftPlan<N, T>::R3) &&
+    static constexpr bool kFusedMac = !kEqOnly && (T == 32) && (FftPlan<N, T>::kPasses == 3) && (FftPlan<N, T>::R1 == FftPlan<N, T>::R3) &&
                                       (N / FftPlan<N, T>::R3 == 2 * T);
     static constexpr int kWorkers = kEqThreads + G * T;       // threads that take part in the EMPTY barriers
     static constexpr int kFullCount = kWorkers + 32;          // ... and in the FULL barriers: the staging warp listens in
@@ -424,7 +434,7 @@ template <int N, int G, int V = 0> struct RenderSmem {
     template <int F> static constexpr int kConvWarpId = place().conv_warp_id[F];
     static constexpr int kStagerWarpId = place().stager_warp_id;
     static constexpr size_t kTwOff = 0;                                      // float2 tw[N]
-    static constexpr size_t kZOff = kTwOff + sizeof(float2) * N;             // float2 z[G][2][NP]
+    static constexpr size_t kZOff = kTwOff + (kEqOnly ? 0 : sizeof(float2) * N);   // float2 z[G][2][NP]
     // per-stream strides carry a 16-byte pad so that neighbouring streams sit on different banks
     // planar ring[G][3 slots][left row | pad | right row | pad]: streams 16 bytes apart in bank space, a stream's two
     // rows 64 bytes apart, so the six rows an EQ warp stores to in one instruction sit on different banks
@@ -436,10 +446,10 @@ template <int N, int G, int V = 0> struct RenderSmem {
     static constexpr int kStageBufs = 3;
     static constexpr int kRowR = B + 4;              // offset of the right row behind the left row
     static constexpr int kStageStride = 2 * B + 8;   // float per stream and stage buffer
-    static constexpr size_t kRingOff = kZOff + sizeof(float2) * G * 2 * NP;
+    static constexpr size_t kRingOff = kZOff + (kEqOnly ? 0 : sizeof(float2) * G * 2 * NP);
     static constexpr size_t kStageOff = kRingOff + sizeof(float) * G * kRingStride;
     // filter spectra of a shared single-set, few-partition HRIR (configs 1-3) are staged here once per launch
-    static constexpr size_t kFiltSmemBytes = (N <= 512) ? 16 * 1024 : 0;
+    static constexpr size_t kFiltSmemBytes = (N <= 512 && !kEqOnly) ? 16 * 1024 : 0;
     static constexpr size_t kFiltOff = kStageOff + sizeof(float) * kStageBufs * G * kStageStride;
     static constexpr size_t kMbarOff = kFiltOff + kFiltSmemBytes;  // uint64_t stage_full[3], filt_full[2], prologue_full
     static constexpr size_t kBytes = kMbarOff + 48;
@@ -807,6 +817,7 @@ __device__ __forceinline__ bool first_block_by_tma(const RenderParams& p, int B)
 template <int N, int G, int V>
 __device__ __forceinline__ void stager_warp_main(const RenderParams& p, unsigned char* smem, int stream0) {
     using SM = RenderSmem<N, G, V>;
+    const bool conv_on = !SM::kEqOnly && p.conv_enable != 0;   // compile-time false in the EQ-only variant: its transforms are dead code
     constexpr int B = SM::B;
     const int n_str = (p.n_streams - stream0) < G ? (p.n_streams - stream0) : G;
     const int row = threadIdx.x & 31;   // 2G <= 14 rows
@@ -829,9 +840,9 @@ __device__ __forceinline__ void stager_warp_main(const RenderParams& p, unsigned
     // block-0 input rows and overlap-save history rows (conv_warps_main); blocks 1 and 2 follow from here.
     {
         uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kMbarOff);
-        const unsigned tw_bytes = (unsigned)(sizeof(float2) * N);
-        const unsigned filt_bytes = (unsigned)(p.filt_in_smem * N * sizeof(float4));
-        const unsigned hist_bytes = p.conv_enable ? (unsigned)(n_str * 2 * B * sizeof(float)) : 0u;
+        const unsigned tw_bytes = SM::kEqOnly ? 0u : (unsigned)(sizeof(float2) * N);
+        const unsigned filt_bytes = SM::kEqOnly ? 0u : (unsigned)(p.filt_in_smem * N * sizeof(float4));
+        const unsigned hist_bytes = conv_on ? (unsigned)(n_str * 2 * B * sizeof(float)) : 0u;
         if (row == 0) {
             mbar_init(&bars[0], 1);   // stage_full[0..2]: input rows of block t in stage buffer t % 3
             mbar_init(&bars[1], 1);
@@ -849,7 +860,7 @@ __device__ __forceinline__ void stager_warp_main(const RenderParams& p, unsigned
         bar_arrive(kBarInitEq, 32 + SM::kEqThreads);
         OHS_STAMP_IF(row == 0, p, 10);
         if (row == 0) {
-            tma_load_1d(smem + SM::kTwOff, p.tw, tw_bytes, &bars[5]);
+            if (tw_bytes) tma_load_1d(smem + SM::kTwOff, p.tw, tw_bytes, &bars[5]);
             // the fused single-partition path reads bin k at position k: its table lands in stream 0's (idle) FFT buffers
             // and the convolution warps permute it into place; every other path keeps the global even-bins-first layout
             if (filt_bytes) tma_load_1d(smem + (SM::kFusedMac && p.filt_in_smem == 1 ? SM::kZOff : SM::kFiltOff), p.filt, filt_bytes, &bars[5]);
@@ -909,6 +920,7 @@ struct OutputStore {
 template <int N, int G, int V>
 __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned char* smem, int stream0, int conv_index) {
     using SM = RenderSmem<N, G, V>;
+    const bool conv_on = !SM::kEqOnly && p.conv_enable != 0;   // compile-time false in the EQ-only variant: its transforms are dead code
     constexpr int B = SM::B, T = SM::T, NP = SM::NP;
     constexpr int kCount = SM::kWorkers;
     using Pl = FftPlan<N, T>;
@@ -935,11 +947,11 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
         nparts = p.set_parts[set];
         filt = p.filt_in_smem ? reinterpret_cast<const float4*>(smem + SM::kFiltOff) : p.filt + (size_t)set * p.pmax * N;
         filt_g = p.filt + (size_t)set * p.pmax * N;
-        gain = p.stream_gain[s];
+        gain = SM::kEqOnly ? 1.f : p.stream_gain[s];   // the EQ pre-pass hands the filtered samples on as they are
         fdl_s = p.fdl + (size_t)s * p.pmax * N;
     }
-    float* out_l = p.out + ((size_t)(s - p.io_first_stream) * 2) * p.row_stride;
-    float* out_r = out_l + p.row_stride;
+    float* out_l = p.out + ((size_t)(s - p.io_first_stream) * 2) * p.out_row_stride;
+    float* out_r = out_l + p.out_row_stride;
     auto stream_sync = [&]() { if (T > 32) bar_sync(kBarStream0 + g, T); else __syncwarp(); };
     // the delay line, the history rows and possibly the input rows are what the previous launch wrote
     grid_dependency_wait();
@@ -951,7 +963,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
         if (first_block_by_tma(p, B))
             tma_load_1d(reinterpret_cast<float*>(smem + SM::kStageOff) + g * SM::kStageStride + tid * SM::kRowR,
                         p.in + ((size_t)(s - p.io_first_stream) * 2 + tid) * p.row_stride, (unsigned)(B * sizeof(float)), &bars[0]);
-        if (p.conv_enable)
+        if (conv_on)
             tma_load_1d(ring_g + 2 * SM::kRingSlot + tid * SM::kRingRowR, reinterpret_cast<const float*>(p.prev) + ((size_t)s * 2 + tid) * B,
                         (unsigned)(B * sizeof(float)), &bars[5]);
     }
@@ -976,7 +988,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     unsigned filt_phase[2] = {0u, 0u};
     constexpr bool kTmaFilterPath = (G >= 2) && (N >= 1024);  // compiled only where long responses live (register budget)
     if (kTmaFilterPath && p.uniform_set && !valid) nparts = p.set_parts[0];  // threads of an absent stream still run the tile loop
-    const bool tma_filters = kTmaFilterPath && p.uniform_set && !p.filt_in_smem && p.conv_enable && nparts > 1;
+    const bool tma_filters = kTmaFilterPath && p.uniform_set && !p.filt_in_smem && conv_on && nparts > 1;
     // one delay-line partition's worth of operands of a bin pair: Z[k], Z[k+1], Z[mirror k], Z[mirror k+1] and their filters
     struct Operands { float4 uu; float2 v0, v1; float4 f0, f1, g0, g1; };
     // a partition's filter table is stored even bins first, odd bins behind them (setup_filters_kernel): a warp's loads
@@ -1076,7 +1088,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
                 }
             }
         } }
-        if (!tma_filters && valid && p.conv_enable && nparts > 1 && !p.spectra_only) {
+        if (!tma_filters && valid && conv_on && nparts > 1 && !p.spectra_only) {
 #pragma unroll 1
             for (int m = 0; m < kPairs; ++m) {
                 const int k = 2 * (tid + m * T);
@@ -1116,7 +1128,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
             if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount);
             continue;
         }
-        if (!p.conv_enable) {
+        if (!conv_on) {
             // EQ + gain only (StereoParametricEQ::process_block followed by the gain loop)
             const int nb = (t == p.n_blocks - 1) ? p.tail_frames : B;
             for (int n = tid; n < nb; n += T) {
@@ -1232,7 +1244,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
     }
     OHS_STAMP_IF(ft == 0, p, 6);
     // overlap-save history for the next launch: the last filtered block
-    if (valid && p.conv_enable && p.n_blocks > 0) {
+    if (valid && conv_on && p.n_blocks > 0) {
         const float* xc = ring_g + ((p.n_blocks - 1) % 3) * SM::kRingSlot;
         float* hl = reinterpret_cast<float*>(p.prev) + (size_t)s * 2 * B;
         for (int n = 4 * tid; n < B; n += 4 * T) {

@@ -13,7 +13,8 @@ struct RenderLaunch {
     int device;            // for the once-per-device function attributes
     cudaStream_t stream;
     int first_stream;      // the launch renders streams [first_stream, n_streams) of RenderParams
-    bool latency_variant;  // RenderSmem V = 1: launches of one or two blocks (ignored where that variant does not exist)
+    int variant;           // RenderSmem V: 0 throughput, 1 latency (launches of one or two blocks; N = 512, else ignored),
+                           // 2 EQ-only pre-pass of the time-batched route (N = 512 only: render_launch_512)
     bool dependent;        // programmatic dependent launch: this grid may start while the previous launch on the stream
                            // drains; the kernel waits (griddepcontrol.wait) before it touches stream state
 };

@@ -46,12 +46,19 @@ template <int G, int V> cudaError_t launch_gv(const RenderLaunch& L, const Rende
     }
 }
 
-// the latency variant (RenderSmem, V = 1) where it exists and fits, else the throughput variant
+// the latency variant (RenderSmem, V = 1) where it exists and fits, else the throughput variant; the EQ-only variant
+// (V = 2) on request
 template <int G> cudaError_t launch_g(const RenderLaunch& L, const RenderParams& p) {
     if constexpr (N == 512) {
-        if constexpr (RenderSmem<N, G, 1>::kFits) {
-            if (L.latency_variant) return launch_gv<G, 1>(L, p);
+        if (L.variant == 2) {
+            if constexpr (RenderSmem<N, G, 2>::kFits) return launch_gv<G, 2>(L, p);
+            else return cudaErrorInvalidConfiguration;
         }
+        if constexpr (RenderSmem<N, G, 1>::kFits) {
+            if (L.variant == 1) return launch_gv<G, 1>(L, p);
+        }
+    } else {
+        if (L.variant == 2) return cudaErrorInvalidConfiguration;
     }
     return launch_gv<G, 0>(L, p);
 }

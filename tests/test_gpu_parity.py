@@ -587,6 +587,46 @@ def test_time_batched_long_response(block, taps, n_streams, n_blocks, monkeypatc
     assert float(np.max(np.abs(y_mixed - ref))) <= TOL
 
 
+@pytest.mark.parametrize("case", ["in_place", "eq_off", "disabled_band", "ragged_prepass"])
+def test_time_batched_pipeline_variants(case, monkeypatch):
+    """The time-batched route's EQ pre-pass pipeline through ohs_process_device: several sub-launches and chunks per call
+    (150 blocks: 8+8+16+32, 64, 22), in place; the EQ off (the transforms read a copy of the input rows); a disabled band
+    (the pre-pass leaves its continuous chain); block 64 with a chunk that is not a whole number of the pre-pass's
+    256-frame rows.  Each against the oracle, and the overlapped pipeline against the same kernels run on one stream
+    (OHS_TB_OVERLAP=0): bit-identical."""
+    import torch
+
+    block, taps, n_streams, n_blocks = {"in_place": (128, 1500, 5, 150), "eq_off": (128, 1100, 4, 70), "disabled_band": (256, 2100, 4, 30),
+                                        "ragged_prepass": (64, 600, 3, 27)}[case]
+    h = S.synthetic_hrir_set(taps, taps / 5.0, seed=23)
+    n = block * n_blocks
+    x = S.stream_inputs(n_streams, n, base_seed=1250)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL)
+    enabled = [1] * 10
+    if case == "disabled_band":
+        enabled[4] = 0
+    ref = oracle_render(x, block, h, None if case == "eq_off" else coeffs, None if case == "eq_off" else enabled, 0.7)
+    outs = {}
+    for overlap in ("1", "0"):
+        monkeypatch.setenv("OHS_TB_OVERLAP", overlap)
+        e = ohs.Engine(n_streams, block, taps)
+        e.set_hrir_set(h); e.set_gain(0.7)
+        if case != "eq_off":
+            for b in range(10):
+                e.eq_set_band(b, coeffs[b], bool(enabled[b]))
+            e.set_eq_enable(True)
+        buf = torch.from_numpy(x).cuda()
+        dst = buf if case == "in_place" else torch.empty_like(buf)
+        # two calls: the second starts from the first one's state (ring head, overlap-save block, EQ state)
+        cut = 16 * block
+        e.process_device(buf.data_ptr(), dst.data_ptr(), cut, row_stride=n)
+        e.process_device(buf.data_ptr() + 4 * cut, dst.data_ptr() + 4 * cut, n - cut, row_stride=n)
+        e.sync()
+        outs[overlap] = dst.cpu().numpy()
+        assert float(np.max(np.abs(outs[overlap] - ref))) <= TOL, (case, overlap)
+    assert np.array_equal(outs["0"], outs["1"])
+
+
 def test_time_batched_mixed_hrir_sets(monkeypatch):
     """Two HRIR sets on one engine, a long one (10 partitions) and a single-partition one, streams bound alternately:
     the time-batched route renders both kinds (a single-partition stream has no delay line of its own)."""
