@@ -111,6 +111,9 @@ struct ohs_engine {
     cudaEvent_t ev_call = nullptr;           // everything enqueued on the engine's stream before this call
     size_t eq_events_used = 0;
     int tb_overlap = 1;      // OHS_TB_OVERLAP=0: EQ pre-pass on the engine's stream, one chunk per sub-launch (A/B)
+    int tb_eq_g = 0;         // OHS_TB_EQ_G: streams per CTA of the EQ pre-pass (A/B)
+    int tb_eq_smem_kb = -1;  // OHS_TB_EQ_SMEM_KB: dynamic shared memory its CTAs ask for at least (A/B; -1: by shape)
+    int tb_chunk = 0;        // OHS_TB_CHUNK=n: uniform chunks of n blocks instead of the ramped schedule (A/B)
 
     // FIFO adaptor (src/dsp/convolution.rs:141-182)
     std::vector<float> fifo_in, fifo_out;  // [row][cap]
@@ -124,7 +127,7 @@ using namespace ohs;
 int launch_render(ohs_engine* h, const RenderParams& p, int first_stream = 0) {
     // few blocks per launch: nothing overlaps inside the launch, so the variant built for latency runs it
     const bool latency = p.n_blocks <= h->latency_blocks && !p.spectra_only;
-    RenderLaunch L{h->G, h->cfg.device, h->stream, first_stream, latency ? 1 : 0, h->dependent_launch};
+    RenderLaunch L{h->G, h->cfg.device, h->stream, first_stream, latency ? 1 : 0, 0, h->dependent_launch};
     RenderParams q = p;
     q.trace = h->d_trace;
     cudaError_t e = cudaErrorInvalidValue;
@@ -375,7 +378,7 @@ template <int N> int launch_inverse(ohs_engine* h, const float2* d_w, float* d_o
         OHS_CUDA(cudaFuncSetAttribute(inverse_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         once.mark(dev);
     }
-    inverse_kernel<N><<<dim3(K, h->cfg.n_streams), fft_threads(N), smem, h->stream>>>(d_w, d_out, h->d_tw, h->d_stream_gain, K,
+    inverse_kernel<N><<<dim3(K, h->cfg.n_streams), SetupSmem<N>::TX, smem, h->stream>>>(d_w, d_out, h->d_tw, h->d_stream_gain, K,
                                                                                       (long long)row_stride);
     OHS_CUDA(cudaGetLastError());
     h->launches++;
@@ -391,7 +394,7 @@ template <int N> int launch_forward(ohs_engine* h, const float* xf, long long xf
         OHS_CUDA(cudaFuncSetAttribute(forward_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         once.mark(dev);
     }
-    forward_kernel<N><<<dim3(k, h->cfg.n_streams), fft_threads(N), smem, h->stream>>>(
+    forward_kernel<N><<<dim3(k, h->cfg.n_streams), SetupSmem<N>::TX, smem, h->stream>>>(
         xf, xf_stride, t0, reinterpret_cast<const float*>(h->d_prev), h->d_zlin, zstride, zbase, h->d_fdl, h->pmax, h->head, ring_from,
         h->d_stream_hrir, h->d_set_parts, h->d_tw);
     OHS_CUDA(cudaGetLastError());
@@ -483,7 +486,18 @@ int launch_eq_prepass(ohs_engine* h, const RenderParams& base, const float* d_in
     q.tail_frames = (int)(frames - (size_t)(q.n_blocks - 1) * kB);
     q.conv_enable = 0; q.eq_enable = 1; q.spectra_only = 0; q.zlin = nullptr; q.filt_in_smem = 0;
     q.trace = nullptr;
-    RenderLaunch L{3, h->cfg.device, stream, 0, 2, h->dependent_launch};
+    // Shape of the pre-pass (RenderSmem, V = 2).  Many streams, run beside the previous chunk's kernels: six per CTA — four
+    // EQ warps, one per scheduler partition — and 200 KB of shared memory asked for, so that each CTA OWNS its SM: next to
+    // the per-bin kernel's FMA-saturated warps every instruction of the biquad chain waits for its issue slot and the
+    // chain, the route's critical path, runs 2.5x slower (measured; config 5 at 256 blocks per call: 4.95 ms with 43 SMs
+    // owned, 5.65 ms with thin CTAs of three streams sharing 86 SMs, 5.82 ms with twelve streams = two EQ warps per
+    // partition on 22 SMs).  Few streams or one stream of work: thin CTAs of three.
+    const bool own_sm = stream != h->stream && h->cfg.n_streams >= 12;
+    const int g = (h->tb_eq_g > 0) ? h->tb_eq_g : (own_sm ? 6 : 3);
+    const size_t min_smem = (h->tb_eq_smem_kb >= 0) ? (size_t)h->tb_eq_smem_kb << 10 : (own_sm ? (size_t)200 << 10 : 0);
+    // no programmatic dependent launch here: the next chunk's CTAs, started early, would sit on SMs of their own (they
+    // cannot share one with this chunk's) and take them from the transforms of the chunk before
+    RenderLaunch L{g, h->cfg.device, stream, 0, 2, min_smem, false};
     const cudaError_t e = render_launch_512(L, q);
     if (e != cudaSuccess) return fail(OHS_ERR_CUDA, "EQ pre-pass launch failed: %s", cudaGetErrorString(e));
     h->launches++;
@@ -505,19 +519,38 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
     const bool overlap = eq_on && h->tb_overlap;
     cudaStream_t eqs = overlap ? h->eq_stream : h->stream;
     const int n_sub = (total + (int)kc - 1) / (int)kc;
-    // chunks of sub-launch j: (first block inside the sub-launch, blocks)
+    // chunks of sub-launch j: (first block inside the sub-launch, blocks).  The EQ pre-pass of a chunk runs beside the
+    // transforms of the chunk before it, so what a call cannot hide is the pre-pass of its first chunk and the transforms of
+    // its last: the first sub-launch ramps up (8, 8, 16, ...), the last one ramps down (..., 16, 8, 8), everything between
+    // goes in the largest pieces (fewer launches, 16 blocks per thread in the per-bin kernel)
     auto chunks_of = [&](int j, std::vector<std::pair<int, int>>& out) {
         out.clear();
         const int k = std::min<int>((int)kc, total - j * (int)kc);
-        if (!overlap || j > 0 || k < 24) { out.emplace_back(0, k); return; }
-        int at = 0;
-        for (int c : {8, 8, 16, 32}) {
-            if (k - at < 2 * c && k - at >= 8) { out.emplace_back(at, k - at); at = k; break; }
-            out.emplace_back(at, c); at += c;
-            if (at >= k) break;
+        if (!overlap) { out.emplace_back(0, k); return; }
+        if (h->tb_chunk > 0) {
+            for (int at = 0; at < k; at += h->tb_chunk) out.emplace_back(at, std::min(h->tb_chunk, k - at));
+            return;
         }
-        if (at < k) out.emplace_back(at, k - at);
+        std::vector<int> head, tail;
+        int rest = k;
+        if (j == 0) for (int c : {8, 8, 16}) if (rest >= 2 * c) { head.push_back(c); rest -= c; }
+        if (j == n_sub - 1) for (int c : {8, 8, 16}) if (rest >= 2 * c) { tail.push_back(c); rest -= c; }
+        int at = 0;
+        for (int c : head) { out.emplace_back(at, c); at += c; }
+        if (rest > 0) { out.emplace_back(at, rest); at += rest; }
+        for (size_t i = tail.size(); i-- > 0;) { out.emplace_back(at, tail[i]); at += tail[i]; }
     };
+#ifdef OHS_TB_TRACE   // debug builds only: a timing event behind every kernel of the route, printed as a timeline per call
+    struct Mark { cudaEvent_t ev; const char* what; int a, b; };
+    std::vector<Mark> marks;
+    auto mark = [&](cudaStream_t st, const char* what, int a, int b) {
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); marks.push_back({e, what, a, b});
+    };
+#define OHS_TB_MARK(st, what, a, b) mark(st, what, a, b)
+#else
+#define OHS_TB_MARK(st, what, a, b) do { } while (0)
+#endif
+    OHS_TB_MARK(h->stream, "call", 0, 0);
     std::vector<std::vector<std::pair<int, int>>> chunks(n_sub);
     std::vector<std::vector<cudaEvent_t>> done_ev(n_sub);
     for (int j = 0; j < n_sub; ++j) chunks_of(j, chunks[j]);
@@ -540,6 +573,7 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
             const size_t f0 = ((size_t)j * kc + c.first) * B;
             int rc = launch_eq_prepass(h, p, d_in + f0, (long long)row_stride, xf + (size_t)c.first * B, xstride, (size_t)c.second * B, eqs);
             if (rc) return rc;
+            OHS_TB_MARK(eqs, "eq", j, c.first);
             if (overlap) {
                 cudaEvent_t ev;
                 rc = next_event(&ev);
@@ -562,6 +596,7 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
         gather_history_kernel<<<dim3((unsigned)hist, (unsigned)S), 256, 0, h->stream>>>(h->d_fdl, h->d_zlin, (int)N, h->pmax, h->head, zstride);
         OHS_CUDA(cudaGetLastError());
         h->launches++;
+        OHS_TB_MARK(h->stream, "gather", j, 0);
         // filtered rows of this sub-launch: a half of d_xf (with the EQ off, a copy of the input rows: the transforms read
         // a block's predecessor too, which an in-place call has overwritten with output by then)
         const float* xf = h->d_xf + (size_t)(j & 1) * xhalf;
@@ -583,9 +618,11 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
                 default: rc = fail(OHS_ERR_INVALID, "unsupported transform size %d", h->N);
             }
             if (rc) return rc;
+            OHS_TB_MARK(h->stream, "forward", j, c0);
             float2* w = h->d_wlin + S * (size_t)c0 * N;
             rc = launch_bin_conv(h, h->d_zlin + (size_t)c0 * N, w, ck, zstride);
             if (rc) return rc;
+            OHS_TB_MARK(h->stream, "bin_conv", j, c0);
             float* out_c = out_j + (size_t)c0 * B;
             switch (h->N) {
                 case 128: rc = launch_inverse<128>(h, w, out_c, ck, row_stride); break;
@@ -596,6 +633,7 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
                 default: rc = fail(OHS_ERR_INVALID, "unsupported transform size %d", h->N);
             }
             if (rc) return rc;
+            OHS_TB_MARK(h->stream, "inverse", j, c0);
         }
         // overlap-save history of the next sub-launch or call: this one's last filtered block
         OHS_CUDA(cudaMemcpy2DAsync(h->d_prev, B * sizeof(float), xf + (size_t)(k - 1) * B, (size_t)xs * sizeof(float), B * sizeof(float),
@@ -606,6 +644,16 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
         }
         h->head = (int)(((size_t)h->head + k) % (size_t)h->pmax);
     }
+#ifdef OHS_TB_TRACE
+    cudaStreamSynchronize(h->stream);
+    if (h->eq_stream) cudaStreamSynchronize(h->eq_stream);
+    for (const Mark& m : marks) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, marks[0].ev, m.ev);
+        fprintf(stderr, "tb_trace %-8s sub %d block %2d done at %8.1f us\n", m.what, m.a, m.b, ms * 1e3);
+    }
+    for (const Mark& m : marks) cudaEventDestroy(m.ev);
+#endif
     return OHS_OK;
 }
 
@@ -646,6 +694,9 @@ int ohs_create(const ohs_config* cfg, ohs_engine** out) {
     h->G = pick_streams_per_cta(h);
     if (const char* e = getenv("OHS_TIME_BATCH")) h->time_batch = atoi(e) != 0;
     if (const char* e = getenv("OHS_TB_OVERLAP")) h->tb_overlap = atoi(e) != 0;
+    if (const char* e = getenv("OHS_TB_EQ_G")) { const int g = atoi(e); if (g == 3 || g == 6) h->tb_eq_g = g; }
+    if (const char* e = getenv("OHS_TB_EQ_SMEM_KB")) { const int k = atoi(e); if (k >= 0 && k <= 227) h->tb_eq_smem_kb = k; }
+    if (const char* e = getenv("OHS_TB_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= 64) h->tb_chunk = c; }
     if (const char* e = getenv("OHS_STAGE_MB")) { const long mb = atol(e); if (mb >= 1 && mb <= 4096) h->stage_bytes = (size_t)mb << 20; }
     if (const char* e = getenv("OHS_PDL")) h->dependent_launch = atoi(e) != 0;
     if (const char* e = getenv("OHS_LATENCY_BLOCKS")) h->latency_blocks = atoi(e);

@@ -8,12 +8,20 @@
 
 namespace ohs {
 
+// Threads per transform of the stand-alone forward and inverse kernels: twice the render kernel's where that keeps the
+// radix plan (8 points per thread instead of 16: same butterflies, same twiddles, bit-identical spectra), because these
+// kernels are bound by memory latency and want warps, not registers
+constexpr int xform_threads(int n) { return (n / fft_threads(n) >= 16) ? 2 * fft_threads(n) : fft_threads(n); }
+
 // ---------------------------------------------------------------------------------------------------------------
 // HRIR set-up: ConvolutionEngine::set_ir (src/dsp/convolution.rs:111-139) for one (set, partition) per CTA.
 // ir: [set][4][pmax*B] zero-padded time-domain taps; filt: [set][pmax][N]
 // ---------------------------------------------------------------------------------------------------------------
 template <int N> struct SetupSmem {
     static constexpr int T = fft_threads(N);
+    static constexpr int TX = xform_threads(N);   // the stand-alone forward and inverse kernels of the time-batched route
+    static_assert(FftPlan<N, TX>::R1 == FftPlan<N, T>::R1 && FftPlan<N, TX>::R2 == FftPlan<N, T>::R2 && FftPlan<N, TX>::R3 == FftPlan<N, T>::R3 &&
+                  FftPlan<N, TX>::R4 == FftPlan<N, T>::R4, "same radix plan, hence bit-identical transforms");
     static constexpr int NP = padded_len(N);
     static constexpr size_t kBytes = sizeof(float2) * (N + 4 * NP);
 };
@@ -86,42 +94,88 @@ __global__ void gather_history_kernel(const float2* __restrict__ fdl, float2* __
 // stream's spectra (32 couples x 8 bytes contiguous per load).  The window of TB spectra lives in shared memory, one
 // 16-byte column entry per thread and slot (slot = time mod TB), so the step loop needs no unrolling over the
 // window's rotation: fully unrolled it is 90 KB of code and the kernel stalls on instruction fetch.
+// Two steps (partitions q and q+1) per iteration: the window value of time tau meets tap q in block tau+q and tap q+1 in
+// block tau+q+1, so every value read from the shared-memory window feeds 32 FMAs instead of 16 — the per-step form
+// spent as many shared-memory wavefront cycles as FMA issue cycles (16 LDS.128 per 256 FMAs per thread).  The value of
+// time t0-q-1, which block t0 needs for tap q+1, is the one that has just been loaded from the time-ordered buffer and
+// is still in registers.  An odd last partition runs the single step.
 template <int TB, bool kDc>
 __device__ __forceinline__ void bin_conv_steps(float2 (&a0)[TB], float2 (&a1)[TB], float4* win, const float4* __restrict__ f,
                                                const float2* __restrict__ z, int N, int nparts, int t0, int f0i, int f1i,
                                                int k0, int k1) {
-    // operands are loaded two steps ahead (a step is ~350 instructions, less than a loaded HBM round trip):
-    // fa/fb and (fa1, fb1, n0, n1) are the taps of steps q and q+1 and the spectrum that enters the window for step q+1
-    float4 fa = f[f0i], fb = f[f1i], fa1 = fa, fb1 = fb;
-    float2 n0 = make_float2(0.f, 0.f), n1 = n0;
-    if (1 < nparts) {
-        fa1 = f[(size_t)N + f0i]; fb1 = f[(size_t)N + f1i];
-        n0 = z[((long long)t0 - 1) * N + k0]; n1 = z[((long long)t0 - 1) * N + k1];
-    }
-#pragma unroll 1
-    for (int q = 0; q < nparts; ++q) {
-        float4 fa2 = fa1, fb2 = fb1;
-        float2 m0 = make_float2(0.f, 0.f), m1 = m0;
-        if (q + 2 < nparts) {
-            const long long tau = (long long)t0 - q - 2;   // the spectrum that enters the window for step q+2
-            fa2 = f[(size_t)(q + 2) * N + f0i]; fb2 = f[(size_t)(q + 2) * N + f1i];
-            m0 = z[tau * N + k0]; m1 = z[tau * N + k1];
+    // One iteration's operands: the taps of partitions q and q+1 for the thread's two bins, and the spectra of times
+    // t0-q-1 and t0-q-2, which enter the window behind them.  They are loaded one iteration ahead (an iteration is ~570
+    // instructions, more than a loaded HBM round trip) into the register set the other iteration does not use (the
+    // loop is unrolled by two by hand: no register moves), through running pointers (no index arithmetic).
+    struct Ops { float4 fa0, fb0, fa1, fb1, n0, n1; };
+    const float4* pf0 = f + f0i;
+    const float4* pf1 = f + f1i;
+    const float2* pz0 = z + ((long long)t0 - 1) * N + k0;
+    const float2* pz1 = z + ((long long)t0 - 1) * N + k1;
+    const long long N2 = 2ll * N;
+    auto load = [&](Ops& o, int q) {
+        if (q < nparts) { o.fa0 = pf0[0]; o.fb0 = pf1[0]; }
+        if (q + 1 < nparts) {
+            o.fa1 = pf0[N]; o.fb1 = pf1[N];
+            const float2 x = pz0[0], y = pz1[0];
+            o.n0 = make_float4(x.x, x.y, y.x, y.y);
         }
+        if (q + 2 < nparts) {
+            const float2 x = pz0[-(long long)N], y = pz1[-(long long)N];
+            o.n1 = make_float4(x.x, x.y, y.x, y.y);
+        }
+        pf0 += N2; pf1 += N2; pz0 -= N2; pz1 -= N2;
+    };
+    auto pair_step = [&](const Ops& o, int q) {
         const int rot = (TB - (q & (TB - 1))) & (TB - 1);   // slot of time t0+tb-q is (tb + rot) mod TB
         const float4* wrot = win + rot * 128;               // every slot is stored twice, TB slots apart: no wrap in the reads
+        {
+            const float2 u0 = make_float2(o.n0.x, o.n0.y), u1 = make_float2(o.n0.z, o.n0.w);   // time t0-q-1, tap q+1, block t0
+            mac_bin(a0[0], u0, kDc ? u0 : u1, o.fa1);
+            mac_bin(a1[0], u1, kDc ? u1 : u0, o.fb1);
+        }
 #pragma unroll
         for (int tb = 0; tb < TB; ++tb) {
             const float4 v = wrot[tb * 128];
             const float2 u0 = make_float2(v.x, v.y), u1 = make_float2(v.z, v.w);
-            mac_bin(a0[tb], u0, kDc ? u0 : u1, fa);   // couple 0 = the two self-mirrored bins 0 and N/2
+            mac_bin(a0[tb], u0, kDc ? u0 : u1, o.fa0);   // couple 0 = the two self-mirrored bins 0 and N/2
+            mac_bin(a1[tb], u1, kDc ? u1 : u0, o.fb0);
+            if (tb + 1 < TB) {
+                mac_bin(a0[tb + 1], u0, kDc ? u0 : u1, o.fa1);
+                mac_bin(a1[tb + 1], u1, kDc ? u1 : u0, o.fb1);
+            }
+        }
+        // the window moves two blocks back: times t0-q-1 and t0-q-2 replace times t0+TB-1-q and t0+TB-2-q
+        const int e1 = (TB - 1 + rot) & (TB - 1), e2 = (TB - 2 + rot) & (TB - 1);
+        win[e1 * 128] = o.n0; win[(e1 + TB) * 128] = o.n0;
+        win[e2 * 128] = o.n1; win[(e2 + TB) * 128] = o.n1;
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    Ops A{zero4, zero4, zero4, zero4, zero4, zero4}, B = A;
+    load(A, 0);
+    const int npairs = nparts >> 1;
+#pragma unroll 1
+    for (int p = 0; p < npairs; p += 2) {
+        load(B, 2 * p + 2);
+        pair_step(A, 2 * p);
+        if (p + 1 < npairs) {
+            load(A, 2 * p + 4);
+            pair_step(B, 2 * p + 2);
+        }
+    }
+    if (nparts & 1) {   // odd partition count: one single step (no later step reads the window)
+        const int q = nparts - 1;
+        const bool in_a = (npairs & 1) == 0;   // the set the last load went to
+        const float4 fa = in_a ? A.fa0 : B.fa0, fb = in_a ? A.fb0 : B.fb0;
+        const int rot = (TB - (q & (TB - 1))) & (TB - 1);
+        const float4* wrot = win + rot * 128;
+#pragma unroll
+        for (int tb = 0; tb < TB; ++tb) {
+            const float4 v = wrot[tb * 128];
+            const float2 u0 = make_float2(v.x, v.y), u1 = make_float2(v.z, v.w);
+            mac_bin(a0[tb], u0, kDc ? u0 : u1, fa);
             mac_bin(a1[tb], u1, kDc ? u1 : u0, fb);
         }
-        {
-            const int e = (TB - 1 + rot) & (TB - 1);        // time t0-q-1 replaces time t0+TB-1-q
-            const float4 nv = make_float4(n0.x, n0.y, n1.x, n1.y);
-            win[e * 128] = nv; win[(e + TB) * 128] = nv;
-        }
-        fa = fa1; fb = fb1; fa1 = fa2; fb1 = fb2; n0 = m0; n1 = m1;
     }
 }
 
@@ -193,12 +247,12 @@ struct SpectrumStore {
 // t >= ring_from (the sub-launch's last pmax blocks) go to the delay-line ring: the blocks of a launch run concurrently,
 // and two blocks pmax apart share a ring slot
 template <int N>
-__global__ void __launch_bounds__(SetupSmem<N>::T) forward_kernel(const float* __restrict__ xf, long long xf_stride, int t0,
+__global__ void __launch_bounds__(SetupSmem<N>::TX) forward_kernel(const float* __restrict__ xf, long long xf_stride, int t0,
                                                                 const float* __restrict__ prev, float2* __restrict__ zlin,
                                                                 long long zlin_stride, int zlin_base, float2* __restrict__ fdl,
                                                                 int pmax, int head, int ring_from, const int* __restrict__ stream_hrir,
                                                                 const int* __restrict__ set_parts, const float2* __restrict__ tw_g) {
-    constexpr int T = SetupSmem<N>::T, NP = SetupSmem<N>::NP, B = N / 2;
+    constexpr int T = SetupSmem<N>::TX, NP = SetupSmem<N>::NP, B = N / 2;
     extern __shared__ __align__(16) unsigned char smem[];
     float2* b0 = reinterpret_cast<float2*>(smem);
     float2* b1 = b0 + NP;
@@ -227,10 +281,10 @@ struct SpectrumSwapLoad {
 
 // one CTA per (block, stream): inverse transform of W_t, last B samples times gain to the output rows
 template <int N>
-__global__ void __launch_bounds__(SetupSmem<N>::T) inverse_kernel(const float2* __restrict__ wlin, float* __restrict__ out,
+__global__ void __launch_bounds__(SetupSmem<N>::TX) inverse_kernel(const float2* __restrict__ wlin, float* __restrict__ out,
                                                                 const float2* __restrict__ tw_g, const float* __restrict__ stream_gain,
                                                                 int K, long long row_stride) {
-    constexpr int T = SetupSmem<N>::T, NP = SetupSmem<N>::NP, B = N / 2;
+    constexpr int T = SetupSmem<N>::TX, NP = SetupSmem<N>::NP, B = N / 2;
     extern __shared__ __align__(16) unsigned char smem[];
     float2* b0 = reinterpret_cast<float2*>(smem);
     float2* b1 = b0 + NP;

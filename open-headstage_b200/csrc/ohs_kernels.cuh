@@ -359,8 +359,12 @@ template <int N> inline void fill_twiddles(float2* out) {
 template <int N, int G, int V = 0> struct RenderSmem {
     // V = 2, N = 512: the EQ-only variant behind the time-batched route's EQ pre-pass (ohs_api.cu): the same staging and
     // EQ warps with one band per lane, "convolution" warps that only copy the filtered rows out, no transform buffers,
-    // twiddles or filter table — a 6-warp CTA with 38 KB of shared memory (G = 3) that runs beside the route's
-    // throughput-bound kernels of the previous chunk instead of in front of them.
+    // twiddles or filter table.  It runs beside the route's throughput-bound kernels of the previous chunk instead of in
+    // front of them — but not on the same SMs: next to the per-bin kernel's FMA-saturated warps every instruction of the
+    // biquad chain waits for its issue slot and the chain runs 2.5x slower (measured), which makes it the critical path
+    // again.  So the production shape is G = 6 (four EQ warps, one per scheduler partition; two per partition run 1.6x
+    // slower per step) with 200 KB of shared memory asked for at launch, so that each CTA OWNS its SM: 43 CTAs for
+    // config 5's 256 streams.  G = 3 (38 KB, six warps) serves few streams and the un-overlapped route.
     static_assert(V == 0 || ((V == 1 || V == 2) && N == 512), "the latency and EQ-only variants exist for N = 512");
     static constexpr bool kEqOnly = (V == 2);
     static constexpr int B = N / 2;
@@ -457,7 +461,7 @@ template <int N, int G, int V = 0> struct RenderSmem {
     // Register budget.  Warps are allocated in groups of four; as many CTAs per SM as shared memory allows (up to
     // four) while every thread keeps at least 80 registers.
     static constexpr int kWarpsAlloc = (kThreads / 32 + 3) / 4 * 4;
-    static constexpr int kBySmem = (int)((227 * 1024) / (kBytes + 1024));
+    static constexpr int kBySmem = kEqOnly ? 1 : (int)((227 * 1024) / (kBytes + 1024));
     static constexpr int kByRegs = 65536 / (80 * 32 * kWarpsAlloc);
     static constexpr int kMinBlocks0 = kBySmem < kByRegs ? kBySmem : kByRegs;
     static constexpr int kMinBlocks = kMinBlocks0 < 1 ? 1 : (kMinBlocks0 > 4 ? 4 : kMinBlocks0);

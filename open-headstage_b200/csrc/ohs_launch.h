@@ -15,6 +15,7 @@ struct RenderLaunch {
     int first_stream;      // the launch renders streams [first_stream, n_streams) of RenderParams
     int variant;           // RenderSmem V: 0 throughput, 1 latency (launches of one or two blocks; N = 512, else ignored),
                            // 2 EQ-only pre-pass of the time-batched route (N = 512 only: render_launch_512)
+    size_t min_smem_bytes; // EQ-only variant: ask for at least this much dynamic shared memory (keeps other kernels' CTAs off the SM)
     bool dependent;        // programmatic dependent launch: this grid may start while the previous launch on the stream
                            // drains; the kernel waits (griddepcontrol.wait) before it touches stream state
 };

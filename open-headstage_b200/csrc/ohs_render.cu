@@ -22,7 +22,7 @@ template <int G, int V> cudaError_t launch_gv(const RenderLaunch& L, const Rende
         // attribute twice is harmless)
         static std::atomic<unsigned char> attr_set[64];
         if (L.device >= 0 && L.device < 64 && !attr_set[L.device].load(std::memory_order_acquire)) {
-            cudaError_t e = cudaFuncSetAttribute(render_kernel<N, G, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kBytes);
+            cudaError_t e = cudaFuncSetAttribute(render_kernel<N, G, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kEqOnly ? 227 * 1024 : (int)SM::kBytes);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(render_kernel<N, G, V>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return e;
@@ -35,7 +35,7 @@ template <int G, int V> cudaError_t launch_gv(const RenderLaunch& L, const Rende
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)((n + G - 1) / G));
         cfg.blockDim = dim3((unsigned)SM::kThreads);
-        cfg.dynamicSmemBytes = SM::kBytes;
+        cfg.dynamicSmemBytes = (SM::kEqOnly && L.min_smem_bytes > SM::kBytes) ? L.min_smem_bytes : SM::kBytes;
         cfg.stream = L.stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
