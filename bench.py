@@ -231,7 +231,7 @@ def run_reference(args, signals):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_json((line))
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -489,7 +489,7 @@ def run_gpu(args, pkg):
 
     if args.device_only:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "gpu_launches": int(launches),
+            emit_json(({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "gpu_launches": int(launches),
                               "note": "device-only run (profiling helper)"}))
         return
 
@@ -580,13 +580,35 @@ def run_gpu(args, pkg):
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_reference_run(pkg.signals, 1, 1, 16 * (os.cpu_count() or 1), 10.24)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
+        emit_json((line))
     ctx.barrier()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner to fd 1
+    when NCCL_DEBUG is set), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
