@@ -316,7 +316,7 @@ def parity_vs_oracle(ctx: Ctx, y_dev, x_host_sample, sample_idx, block, h, coeff
     return float(np.max(np.abs(got - ref)))
 
 
-def run_stream_config(ctx: Ctx, cfg_id: int, k_blocks: int, reps: int, also_blocks: int = 0):
+def run_stream_config(ctx: Ctx, cfg_id: int, k_blocks: int, reps: int, also_blocks=()):
     """BASELINE config 3 or 5: one GPU's share of the streams, K blocks per call, device-resident; parity of 8 sampled
     streams (first call, zero state) against the oracle; roofline by the config's own bytes(K) formula."""
     torch, pkg = ctx.torch, ctx.pkg
@@ -364,14 +364,14 @@ def run_stream_config(ctx: Ctx, cfg_id: int, k_blocks: int, reps: int, also_bloc
                         "frac": bytes_per_call / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_call": int(bytes_per_call),
                         "note": "bytes(K=%d) of SURVEY.md 8d for this config" % k_blocks},
            "parity_max_abs": ctx.max_over_ranks(err), "parity_streams_sampled": int(sample.size), "parity_bar": 1e-5}
-    if also_blocks:
-        # the same engine with fewer blocks per call (the EQ pre-pass of a call's first chunk and the transforms of its last
-        # are not overlapped, so short calls pay more per block)
-        n2 = block * also_blocks
+    # the same engine with fewer blocks per call (the EQ pre-pass of a call's first chunk and the transforms of its last are
+    # not overlapped, so short calls pay more per block)
+    for kb in also_blocks:
+        n2 = block * kb
         for _ in range(2):
             eng.process_device(d_in.data_ptr(), d_out.data_ptr(), n2, row_stride=n)
         ms2 = ctx.timed(stream, lambda: eng.process_device(d_in.data_ptr(), d_out.data_ptr(), n2, row_stride=n), reps)
-        out["at_%d_blocks_per_call" % also_blocks] = {"value": n_streams * ctx.world * (n2 / fs) / (ms2 * 1e-3), "unit": UNIT, "ms_per_call": ms2}
+        out["at_%d_blocks_per_call" % kb] = {"value": n_streams * ctx.world * (n2 / fs) / (ms2 * 1e-3), "unit": UNIT, "ms_per_call": ms2}
     del eng, d_in, d_out
     torch.cuda.empty_cache()
     return out
@@ -533,7 +533,7 @@ def run_gpu(args, pkg):
         del d_in, d_out
         torch.cuda.empty_cache()
         configs["cfg3"] = run_stream_config(ctx, 3, 128, reps=5)
-        configs["cfg5"] = run_stream_config(ctx, 5, 256, reps=4, also_blocks=64)
+        configs["cfg5"] = run_stream_config(ctx, 5, 512, reps=3, also_blocks=(64, 256))
         configs["cfg4"] = run_object_config(ctx, reps=3)
 
     if rank == 0:
