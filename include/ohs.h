@@ -26,7 +26,8 @@
  *   - there is no CPU fallback: if no CUDA device is usable, ohs_create fails.
  *   - the environment is read once, in ohs_create: OHS_STREAMS_PER_CTA (1..7, which render-kernel instantiation the
  *     handle uses; default: chosen from n_streams and the SM count), OHS_TIME_BATCH (0 = ohs_set_time_batch(h, 0)),
- *     OHS_STAGE_MB (staging chunk of the host-pointer path, default 24), OHS_PDL (0 = no programmatic dependent launches).
+ *     OHS_STAGE_MB (staging chunk of the host-pointer path, default 24), OHS_PDL (0 = no programmatic dependent launches),
+ *     OHS_TB_OVERLAP / OHS_TB_CHUNK / OHS_TB_EQ_G / OHS_TB_EQ_SMEM_KB (A/B switches of the time-batched route).
  */
 #ifndef OHS_H
 #define OHS_H
@@ -148,10 +149,11 @@ int ohs_prepare(ohs_engine* h, size_t n_frames, int host_io);
  * blocks, i.e. the zero-latency case of the reference's FIFO (host block = multiple of BLOCK_SIZE).
  * in == out (in place) is allowed.  row_stride = frames between consecutive (stream, channel) rows (>= n_frames).
  * Device flavour: pointers are device memory on cfg.device; the call only enqueues on the engine's stream.
- * Long responses (>= 8 partitions) rendered >= 8 blocks per call take a time-batched route (spectra first, then a
- * per-bin convolution along time, then the inverse transforms; up to 2 GiB of scratch, allocated on first use or by
- * ohs_prepare) with the same results within round-off and the same state afterwards; ohs_set_time_batch(h, 0)
- * disables it. */
+ * Long responses (>= 8 partitions) rendered >= 8 blocks per call take a time-batched route (EQ pre-pass on a second
+ * stream of the handle, one chunk ahead of: forward transforms, a per-bin convolution along time, inverse transforms;
+ * up to 2 GiB of scratch, allocated on first use or by ohs_prepare) with the same results within round-off and the
+ * same state afterwards; the call is still ordered on the engine's stream alone; ohs_set_time_batch(h, 0) disables
+ * it. */
 int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_frames, size_t row_stride);
 /* Host flavour: pointers are host memory (pinned memory from ohs_host_alloc gives full PCIe speed); the call
  * stages time chunks through HBM with copies overlapped against the kernels and returns when `out` is complete. */
