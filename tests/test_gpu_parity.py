@@ -587,17 +587,18 @@ def test_time_batched_long_response(block, taps, n_streams, n_blocks, monkeypatc
     assert float(np.max(np.abs(y_mixed - ref))) <= TOL
 
 
-@pytest.mark.parametrize("case", ["in_place", "eq_off", "disabled_band", "ragged_prepass"])
+@pytest.mark.parametrize("case", ["in_place", "eq_off", "disabled_band", "ragged_prepass", "own_sm"])
 def test_time_batched_pipeline_variants(case, monkeypatch):
     """The time-batched route's EQ pre-pass pipeline through ohs_process_device: several sub-launches and chunks per call
     (150 blocks: 8+8+16+32, 64, 22), in place; the EQ off (the transforms read a copy of the input rows); a disabled band
     (the pre-pass leaves its continuous chain); block 64 with a chunk that is not a whole number of the pre-pass's
-    256-frame rows.  Each against the oracle, and the overlapped pipeline against the same kernels run on one stream
+    256-frame rows; 14 streams, which select the pre-pass's production shape (render_kernel<512,6,2>: six streams per
+    CTA on an SM of its own, here two full CTAs and a partial one).  Each against the oracle, and the overlapped pipeline against the same kernels run on one stream
     (OHS_TB_OVERLAP=0): bit-identical."""
     import torch
 
     block, taps, n_streams, n_blocks = {"in_place": (128, 1500, 5, 150), "eq_off": (128, 1100, 4, 70), "disabled_band": (256, 2100, 4, 30),
-                                        "ragged_prepass": (64, 600, 3, 27)}[case]
+                                        "ragged_prepass": (64, 600, 3, 27), "own_sm": (128, 1100, 14, 80)}[case]
     h = S.synthetic_hrir_set(taps, taps / 5.0, seed=23)
     n = block * n_blocks
     x = S.stream_inputs(n_streams, n, base_seed=1250)
