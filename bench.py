@@ -364,6 +364,24 @@ def run_stream_config(ctx: Ctx, cfg_id: int, k_blocks: int, reps: int, also_bloc
                         "frac": bytes_per_call / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_call": int(bytes_per_call),
                         "note": "bytes(K=%d) of SURVEY.md 8d for this config" % k_blocks},
            "parity_max_abs": ctx.max_over_ranks(err), "parity_streams_sampled": int(sample.size), "parity_bar": 1e-5}
+    # the other side of north_star's roofline ("the slower of FLOPs at FP32 peak and bytes at HBM bandwidth"), per GPU
+    flops_per_call = algorithmic_flops_per_stream_block(block, parts) * k_blocks * n_streams
+    t_hbm, t_fp32 = bytes_per_call / (peak * 1e9), flops_per_call / (FP32_FMA_TFLOPS_MEASURED * 1e12)
+    out["roofline_fp32"] = {"achieved_tflops": flops_per_call / (ms * 1e-3) / 1e12, "peak_tflops_fma_measured": FP32_FMA_TFLOPS_MEASURED,
+                            "frac": flops_per_call / (ms * 1e-3) / 1e12 / FP32_FMA_TFLOPS_MEASURED,
+                            "flops_per_stream_block": algorithmic_flops_per_stream_block(block, parts)}
+    out["binding_roofline"] = {"bound": "fp32" if t_fp32 > t_hbm else "hbm", "frac": max(t_fp32, t_hbm) / (ms * 1e-3),
+                               "note": "time the slower roofline allows / measured time, per GPU"}
+    if "time-batched" in route:
+        # SURVEY.md 8d, restructuring note: the offline pipeline is reported against its OWN byte formula, 16 B + 8 S per
+        # stream-block (audio in and out, one spectrum written, read and its product written and read), not bytes(K)
+        own = (16 * block + 8 * 8 * (block + 1)) * k_blocks * n_streams
+        out["roofline_pipeline"] = {"bound": "hbm", "achieved": own / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": own / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_call": int(own),
+                                    "formula": "(16*B + 8*S) per stream-block, S = 8*(B+1)",
+                                    "measured_dram_bytes_per_stream_block": 131800,
+                                    "measured_note": "ncu launch list of a serialised 64-block call (profiles/r02_ncu_launches_config5_time_batched_k64.csv): "
+                                                     "2.16 GB read + written per 64 blocks of 256 streams"}
     # the same engine with fewer blocks per call (the EQ pre-pass of a call's first chunk and the transforms of its last are
     # not overlapped, so short calls pay more per block)
     for kb in also_blocks:
