@@ -126,7 +126,7 @@ using namespace ohs;
 
 int launch_render(ohs_engine* h, const RenderParams& p, int first_stream = 0) {
     // few blocks per launch: nothing overlaps inside the launch, so the variant built for latency runs it
-    const bool latency = p.n_blocks <= h->latency_blocks && !p.spectra_only;
+    const bool latency = p.n_blocks <= h->latency_blocks;
     RenderLaunch L{h->G, h->cfg.device, h->stream, first_stream, latency ? 1 : 0, 0, h->dependent_launch};
     RenderParams q = p;
     q.trace = h->d_trace;
@@ -484,7 +484,7 @@ int launch_eq_prepass(ohs_engine* h, const RenderParams& base, const float* d_in
     q.in = d_in; q.out = d_out; q.row_stride = in_stride; q.out_row_stride = out_stride;
     q.n_blocks = (int)((frames + kB - 1) / kB);
     q.tail_frames = (int)(frames - (size_t)(q.n_blocks - 1) * kB);
-    q.conv_enable = 0; q.eq_enable = 1; q.spectra_only = 0; q.zlin = nullptr; q.filt_in_smem = 0;
+    q.conv_enable = 0; q.eq_enable = 1; q.filt_in_smem = 0;
     q.trace = nullptr;
     // Shape of the pre-pass (RenderSmem, V = 2).  Many streams, run beside the previous chunk's kernels: six per CTA — four
     // EQ warps, one per scheduler partition — and 200 KB of shared memory asked for, so that each CTA OWNS its SM: next to

@@ -78,10 +78,6 @@ struct RenderParams {
     const float* eqc;           // [eq_set][kMaxBands][kEqCoefStride]
     float4* eqs;                // [stream][kMaxBands] {s1L, s1R, s2L, s2R}
     const float2* tw;           // [N] exp(-2*pi*i*m/N)
-    float2* zlin;               // time-batched mode (ohs_api.cu): [stream][zlin_base + K][N] spectra in time order, else null
-    long long zlin_stride;      // float2 per stream
-    int zlin_base;              // slot of this launch's block 0 (the pmax-1 slots before it hold the gathered history)
-    int spectra_only;           // time-batched mode: the convolution warps stop after the forward transform
     int pmax;
     int head;                   // ring slot of this launch's first block
     int n_bands;
@@ -1027,7 +1023,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
         for (int m = 0; m < kPairs; ++m)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[m][e] = make_float2(0.f, 0.f);
-        if constexpr (kTmaFilterPath) { if (tma_filters && !p.spectra_only) {
+        if constexpr (kTmaFilterPath) { if (tma_filters) {
             // Long impulse response shared by the CTA's streams (config 5): partition q's filter tile (16*N bytes, the
             // same for every stream) is brought into shared memory by ONE TMA bulk copy, double-buffered in the FFT
             // ping-pong buffers of streams 0 and 1 (idle until the forward FFT), while each thread keeps two
@@ -1092,7 +1088,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
                 }
             }
         } }
-        if (!tma_filters && valid && conv_on && nparts > 1 && !p.spectra_only) {
+        if (!tma_filters && valid && conv_on && nparts > 1) {
 #pragma unroll 1
             for (int m = 0; m < kPairs; ++m) {
                 const int k = 2 * (tid + m * T);
@@ -1143,7 +1139,7 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
             continue;
         }
         if constexpr (SM::kFusedMac) {
-            if (nparts == 1 && !p.spectra_only) {
+            if (nparts == 1) {
                 // ---- single partition: forward passes 1 and 2 through shared memory; then the last forward pass, the
                 // spectral product and the first inverse pass in registers.  The last pass's butterfly i produces the
                 // bins i + q*NB (q < R), exactly the inputs of the inverse transform's first-pass butterfly i, and the
@@ -1202,23 +1198,16 @@ __device__ __forceinline__ void conv_warps_main(const RenderParams& p, unsigned 
                       [&]() { if (release) bar_arrive(kBarEmpty0 + (t & 1), kCount); });
         stream_sync();
         // ---- this block's spectrum: into the delay line, and its product with partition 0 on top of the history
-        if (nparts > 1 || p.zlin) {
-            // (a single-partition stream keeps no delay line, but in time-batched mode its spectrum still goes to the
-            // time-ordered buffer: the per-bin kernel computes every stream's products)
-            float4* dstz = nparts > 1 ? reinterpret_cast<float4*>(fdl_s + (size_t)slot * N) : nullptr;
-            float4* dstl = p.zlin ? reinterpret_cast<float4*>(p.zlin + (size_t)s * p.zlin_stride + (size_t)(p.zlin_base + t) * N) : nullptr;
+        if (nparts > 1) {
+            float4* dstz = reinterpret_cast<float4*>(fdl_s + (size_t)slot * N);
 #pragma unroll
             for (int e = 0; e < N / 2 / T; ++e) {
                 const int i = 2 * (tid + e * T);
                 float2 z0, z1;
                 zbuf.ld2(i, z0, z1);
-                if (dstz) dstz[i >> 1] = make_float4(z0.x, z0.y, z1.x, z1.y);
-                if (dstl) dstl[i >> 1] = make_float4(z0.x, z0.y, z1.x, z1.y);
+                dstz[i >> 1] = make_float4(z0.x, z0.y, z1.x, z1.y);
             }
         }
-        // time-batched mode: the products and the inverse transforms of the whole launch follow in bin_conv_kernel and
-        // inverse_kernel
-        if (p.spectra_only) { stream_sync(); continue; }
         // partition 0's spectra come from the resident shared-memory copy (plain LDS: the address space is known at
         // compile time) or from global memory; one generic pointer for both would compile to generic loads
         auto mac_partition0 = [&](const float4* fq) {
