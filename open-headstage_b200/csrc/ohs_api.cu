@@ -102,6 +102,12 @@ struct ohs_engine {
     float2* d_zlin = nullptr;
     float2* d_wlin = nullptr;
     size_t zlin_blocks = 0;  // blocks per sub-launch the two buffers are sized for
+    // The time-ordered buffer is circular (zl_cap = pmax-1 + zlin_blocks slots per stream; zl_base = slot of the next
+    // block) and carries the convolution history from one time-batched call to the next; the delay-line ring d_fdl is
+    // what the block-by-block kernel and the state blob use.  At least one of the two is current at any time; they are
+    // converted into each other (gather / scatter, a copy of pmax-1 spectra per stream) only when the route changes.
+    int zl_base = 0, zl_cap = 0;
+    bool zlin_valid = false, ring_valid = true;
     // ... and its EQ pre-pass: the EQ-filtered rows of two sub-launches (halves used alternately), written by the EQ-only
     // kernel on its own stream while the previous chunk's transforms and products run on the engine's stream
     float* d_xf = nullptr;   // [2 halves][stream][2][zlin_blocks * B]
@@ -188,7 +194,23 @@ int launch_setup(ohs_engine* h, int max_parts, int n_sets) {
     return fail(OHS_ERR_INVALID, "unsupported block size %d", h->B);
 }
 
+// the delay-line ring brought up to date from the time-ordered buffer (after time-batched calls), before anything reads
+// or partially rewrites it
+int ensure_ring(ohs_engine* h) {
+    if (h->ring_valid) return OHS_OK;
+    if (h->pmax > 1 && h->d_zlin) {
+        scatter_history_kernel<<<dim3((unsigned)(h->pmax - 1), (unsigned)h->cfg.n_streams), 256, 0, h->stream>>>(
+            h->d_zlin, h->d_fdl, h->N, h->pmax, h->head, (long long)h->zl_cap * h->N, h->zl_base, h->zl_cap);
+        OHS_CUDA(cudaGetLastError());
+        h->launches++;
+    }
+    h->ring_valid = true;
+    return OHS_OK;
+}
+
 int clear_history(ohs_engine* h, bool only_flagged) {
+    if (only_flagged) { const int rc = ensure_ring(h); if (rc) return rc; }
+    h->ring_valid = true; h->zlin_valid = false;   // the cleared ring is the current history from here on
     clear_history_kernel<<<h->cfg.n_streams, 256, 0, h->stream>>>(h->d_fdl, h->d_prev, h->d_stream_hrir, h->cfg.n_streams,
                                                                  only_flagged ? h->d_set_flags : nullptr,
                                                                  (size_t)h->pmax * h->N, (size_t)h->B);
@@ -387,6 +409,7 @@ template <int N> int launch_inverse(ohs_engine* h, const float2* d_w, float* d_o
 
 // forward transforms of blocks [t0, t0 + k) of a sub-launch from the filtered rows xf (block 0's history: d_prev)
 template <int N> int launch_forward(ohs_engine* h, const float* xf, long long xf_stride, int t0, int k, long long zstride, int zbase, int ring_from) {
+    // zbase: the time-ordered buffer's slot of the sub-launch's block 0
     constexpr size_t smem = sizeof(float2) * 2 * padded_len(N);
     static AttrOnce once;
     const int dev = h->cfg.device;
@@ -395,7 +418,7 @@ template <int N> int launch_forward(ohs_engine* h, const float* xf, long long xf
         once.mark(dev);
     }
     forward_kernel<N><<<dim3(k, h->cfg.n_streams), SetupSmem<N>::TX, smem, h->stream>>>(
-        xf, xf_stride, t0, reinterpret_cast<const float*>(h->d_prev), h->d_zlin, zstride, zbase, h->d_fdl, h->pmax, h->head, ring_from,
+        xf, xf_stride, t0, reinterpret_cast<const float*>(h->d_prev), h->d_zlin, zstride, zbase, h->zl_cap, h->d_fdl, h->pmax, h->head, ring_from,
         h->d_stream_hrir, h->d_set_parts, h->d_tw);
     OHS_CUDA(cudaGetLastError());
     h->launches++;
@@ -430,6 +453,8 @@ int ensure_time_batch_scratch(ohs_engine* h, int n_blocks) {
     kc = std::min<size_t>(std::min<size_t>(kc, 64), (size_t)n_blocks);
     if (kc < (size_t)kTimeBatch) return 1;
     if (kc > h->zlin_blocks) {
+        { const int rc = ensure_ring(h); if (rc) return rc; }   // the history moves to the ring before its buffer goes
+        h->zlin_valid = false;
         OHS_CUDA(cudaStreamSynchronize(h->stream));
         if (h->eq_stream) OHS_CUDA(cudaStreamSynchronize(h->eq_stream));
         if (h->d_zlin) OHS_CUDA(cudaFree(h->d_zlin));
@@ -440,6 +465,7 @@ int ensure_time_batch_scratch(ohs_engine* h, int n_blocks) {
         OHS_CUDA(cudaMalloc(&h->d_wlin, S * kc * N * sizeof(float2)));
         OHS_CUDA(cudaMalloc(&h->d_xf, 2 * S * 2 * kc * (size_t)h->B * sizeof(float)));
         h->zlin_blocks = kc;
+        h->zl_cap = (int)(hist + kc); h->zl_base = (int)hist;
     }
     if (!h->eq_stream) {
         int lo = 0, hi = 0;
@@ -452,8 +478,9 @@ int ensure_time_batch_scratch(ohs_engine* h, int n_blocks) {
     return OHS_OK;
 }
 
-// the per-bin convolution of blocks [0, k) behind time-ordered slot base `z`, products to `w` ([stream][k][N])
-int launch_bin_conv(ohs_engine* h, const float2* z, float2* w, int k, long long zstride) {
+// the per-bin convolution of the k blocks from slot zslot0 of the circular time-ordered buffer on, products to `w`
+// ([stream][k][N])
+int launch_bin_conv(ohs_engine* h, int zslot0, float2* w, int k, long long zstride) {
     const size_t S = (size_t)h->cfg.n_streams, N = (size_t)h->N;
     const dim3 blk(128);
     const unsigned gx = (unsigned)((N / 2 + 31) / 32), gz = (unsigned)((S + 3) / 4);
@@ -467,10 +494,10 @@ int launch_bin_conv(ohs_engine* h, const float2* z, float2* w, int k, long long 
     // than 8 at K = 16 (0.529 vs 0.560 ms), 32, 64 and 128 on config 5
     if (k >= 16)
         bin_conv_kernel<16><<<dim3(gx, (unsigned)((k + 15) / 16), gz), blk, 2 * 16 * 128 * sizeof(float4), h->stream>>>(
-            z, w, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride);
+            h->d_zlin, w, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride, zslot0, h->zl_cap);
     else
         bin_conv_kernel<kTimeBatch><<<dim3(gx, (unsigned)((k + kTimeBatch - 1) / kTimeBatch), gz), blk, 2 * kTimeBatch * 128 * sizeof(float4), h->stream>>>(
-            z, w, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride);
+            h->d_zlin, w, h->d_filt, h->d_stream_hrir, h->d_set_parts, (int)N, h->pmax, k, (int)S, zstride, zslot0, h->zl_cap);
     OHS_CUDA(cudaGetLastError());
     h->launches++;
     return OHS_OK;
@@ -595,10 +622,17 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
     for (int j = 0; j < n_sub; ++j) {
         const int k = std::min<int>((int)kc, total - j * (int)kc);
         if (!overlap) { const int rc = enqueue_eq(j); if (rc) return rc; }
-        gather_history_kernel<<<dim3((unsigned)hist, (unsigned)S), 256, 0, h->stream>>>(h->d_fdl, h->d_zlin, (int)N, h->pmax, h->head, zstride);
-        OHS_CUDA(cudaGetLastError());
-        h->launches++;
-        OHS_TB_MARK(h->stream, "gather", j, 0);
+        if (!h->zlin_valid) {
+            // the route changes here (first call, or block-by-block calls since the last time-batched one): the ring's
+            // history goes behind the next block's slot; between time-batched sub-launches and calls nothing is copied
+            gather_history_kernel<<<dim3((unsigned)hist, (unsigned)S), 256, 0, h->stream>>>(h->d_fdl, h->d_zlin, (int)N, h->pmax, h->head, zstride,
+                                                                                        h->zl_base, h->zl_cap);
+            OHS_CUDA(cudaGetLastError());
+            h->launches++;
+            h->zlin_valid = true;
+            OHS_TB_MARK(h->stream, "gather", j, 0);
+        }
+        const int zb = h->zl_base;   // slot of this sub-launch's block 0
         // filtered rows of this sub-launch: a half of d_xf (with the EQ off, a copy of the input rows: the transforms read
         // a block's predecessor too, which an in-place call has overwritten with output by then)
         const float* xf = h->d_xf + (size_t)(j & 1) * xhalf;
@@ -612,17 +646,17 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
             if (overlap) OHS_CUDA(cudaStreamWaitEvent(h->stream, done_ev[j][ci], 0));
             int rc;
             switch (h->N) {
-                case 128: rc = launch_forward<128>(h, xf, xs, c0, ck, zstride, (int)hist, k - h->pmax); break;
-                case 256: rc = launch_forward<256>(h, xf, xs, c0, ck, zstride, (int)hist, k - h->pmax); break;
-                case 512: rc = launch_forward<512>(h, xf, xs, c0, ck, zstride, (int)hist, k - h->pmax); break;
-                case 1024: rc = launch_forward<1024>(h, xf, xs, c0, ck, zstride, (int)hist, k - h->pmax); break;
-                case 2048: rc = launch_forward<2048>(h, xf, xs, c0, ck, zstride, (int)hist, k - h->pmax); break;
+                case 128: rc = launch_forward<128>(h, xf, xs, c0, ck, zstride, zb, 1 << 30); break;
+                case 256: rc = launch_forward<256>(h, xf, xs, c0, ck, zstride, zb, 1 << 30); break;
+                case 512: rc = launch_forward<512>(h, xf, xs, c0, ck, zstride, zb, 1 << 30); break;
+                case 1024: rc = launch_forward<1024>(h, xf, xs, c0, ck, zstride, zb, 1 << 30); break;
+                case 2048: rc = launch_forward<2048>(h, xf, xs, c0, ck, zstride, zb, 1 << 30); break;
                 default: rc = fail(OHS_ERR_INVALID, "unsupported transform size %d", h->N);
             }
             if (rc) return rc;
             OHS_TB_MARK(h->stream, "forward", j, c0);
             float2* w = h->d_wlin + S * (size_t)c0 * N;
-            rc = launch_bin_conv(h, h->d_zlin + (size_t)c0 * N, w, ck, zstride);
+            rc = launch_bin_conv(h, (zb + c0) % h->zl_cap, w, ck, zstride);
             if (rc) return rc;
             OHS_TB_MARK(h->stream, "bin_conv", j, c0);
             float* out_c = out_j + (size_t)c0 * B;
@@ -645,6 +679,8 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
             if (j + 2 < n_sub) { const int rc = enqueue_eq(j + 2); if (rc) return rc; }
         }
         h->head = (int)(((size_t)h->head + k) % (size_t)h->pmax);
+        h->zl_base = (zb + k) % h->zl_cap;
+        h->ring_valid = false;   // the spectra of these blocks exist in the time-ordered buffer only (ensure_ring)
     }
 #ifdef OHS_TB_TRACE
     cudaStreamSynchronize(h->stream);
@@ -844,6 +880,8 @@ int ohs_bind_stream_hrir(ohs_engine* h, int stream, int hrir_set) {
         if (rc) return rc;
         return clear_history(h, false);
     }
+    { const int rc = ensure_ring(h); if (rc) return rc; }
+    h->zlin_valid = false;
     OHS_CUDA(cudaMemsetAsync(h->d_fdl + (size_t)stream * h->pmax * h->N, 0, sizeof(float2) * (size_t)h->pmax * h->N, h->stream));
     OHS_CUDA(cudaMemsetAsync(h->d_prev + (size_t)stream * h->B, 0, sizeof(float2) * (size_t)h->B, h->stream));
     return OHS_OK;
@@ -1039,9 +1077,13 @@ int ohs_process_device(ohs_engine* h, const float* d_in, float* d_out, size_t n_
         batched = (rc == 0);
     }
     if (!batched) {
+        if (h->conv_enable) { rc = ensure_ring(h); if (rc) return rc; }   // the kernel reads and extends the delay-line ring
         rc = launch_render(h, p);
         if (rc) return rc;
-        if (h->conv_enable) h->head = (int)(((size_t)h->head + p.n_blocks) % (size_t)h->pmax);
+        if (h->conv_enable) {
+            h->head = (int)(((size_t)h->head + p.n_blocks) % (size_t)h->pmax);
+            h->zlin_valid = false;
+        }
     }
     if (h->timing) { OHS_CUDA(cudaEventRecord(h->ev_k1, h->stream)); h->timed = true; }
     return OHS_OK;
@@ -1377,6 +1419,8 @@ int ohs_state_export(ohs_engine* h, void* host_buf, size_t bytes) {
     OHS_CUDA(cudaSetDevice(h->cfg.device));
     int rc = commit_filters(h);
     if (rc) return rc;
+    rc = ensure_ring(h);   // the blob carries the delay-line ring
+    if (rc) return rc;
     OHS_CUDA(cudaStreamSynchronize(h->stream));
     unsigned char* p = (unsigned char*)host_buf;
     const size_t S = h->cfg.n_streams;
@@ -1415,6 +1459,7 @@ int ohs_state_import(ohs_engine* h, const void* host_buf, size_t bytes) {
     const size_t S = h->cfg.n_streams;
     const size_t n0 = sizeof(float2) * S * h->pmax * h->N, n1 = sizeof(float2) * S * h->B, n2 = sizeof(float4) * S * kMaxBands;
     h->head = hdr.head;
+    h->ring_valid = true; h->zlin_valid = false;
     OHS_CUDA(cudaMemcpy(h->d_fdl, p, n0, cudaMemcpyHostToDevice)); p += n0;
     OHS_CUDA(cudaMemcpy(h->d_prev, p, n1, cudaMemcpyHostToDevice)); p += n1;
     OHS_CUDA(cudaMemcpy(h->d_eqs, p, n2, cudaMemcpyHostToDevice)); p += n2;

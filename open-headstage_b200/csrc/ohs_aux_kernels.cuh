@@ -80,13 +80,28 @@ __global__ void __launch_bounds__(SetupSmem<N>::T) setup_filters_kernel(const fl
 // keeps their TB accumulators and a sliding window of TB spectra in registers, and walks q once — one new spectrum
 // value and one filter tap loaded per step for TB*16 FMAs.  A third kernel runs the inverse transforms.
 // ---------------------------------------------------------------------------------------------------------------
-// history of the delay-line ring -> the first pmax-1 slots of the time-ordered buffer (slot pmax-1-q holds time -q)
+// The time-ordered buffer is CIRCULAR in time: `cap` slots per stream, the slot of the next block (`zbase`) moves on
+// by the blocks rendered, and the pmax-1 slots behind it hold the history — so consecutive time-batched sub-launches
+// and calls find their history in place and nothing is copied between them.  The delay-line ring (what the
+// block-by-block kernel reads) and the buffer are converted into each other only when the route changes:
+// ring -> buffer (time -q, q = 1..pmax-1, goes to slot zbase - q) ...
 __global__ void gather_history_kernel(const float2* __restrict__ fdl, float2* __restrict__ zlin, int N, int pmax, int head,
-                                      long long zlin_stride) {
+                                      long long zlin_stride, int zbase, int cap) {
     const int q = blockIdx.x + 1, s = blockIdx.y;
     int sl = head - q; if (sl < 0) sl += pmax;
+    int zs = zbase - q; if (zs < 0) zs += cap;
     const float4* src = reinterpret_cast<const float4*>(fdl + ((size_t)s * pmax + sl) * N);
-    float4* dst = reinterpret_cast<float4*>(zlin + (size_t)s * zlin_stride + (size_t)(pmax - 1 - q) * N);
+    float4* dst = reinterpret_cast<float4*>(zlin + (size_t)s * zlin_stride + (size_t)zs * N);
+    for (int i = threadIdx.x; i < N / 2; i += blockDim.x) dst[i] = src[i];
+}
+// ... and buffer -> ring
+__global__ void scatter_history_kernel(const float2* __restrict__ zlin, float2* __restrict__ fdl, int N, int pmax, int head,
+                                       long long zlin_stride, int zbase, int cap) {
+    const int q = blockIdx.x + 1, s = blockIdx.y;
+    int sl = head - q; if (sl < 0) sl += pmax;
+    int zs = zbase - q; if (zs < 0) zs += cap;
+    const float4* src = reinterpret_cast<const float4*>(zlin + (size_t)s * zlin_stride + (size_t)zs * N);
+    float4* dst = reinterpret_cast<float4*>(fdl + ((size_t)s * pmax + sl) * N);
     for (int i = threadIdx.x; i < N / 2; i += blockDim.x) dst[i] = src[i];
 }
 
@@ -101,30 +116,31 @@ __global__ void gather_history_kernel(const float2* __restrict__ fdl, float2* __
 // is still in registers.  An odd last partition runs the single step.
 template <int TB, bool kDc>
 __device__ __forceinline__ void bin_conv_steps(float2 (&a0)[TB], float2 (&a1)[TB], float4* win, const float4* __restrict__ f,
-                                               const float2* __restrict__ z, int N, int nparts, int t0, int f0i, int f1i,
+                                               const float2* __restrict__ z, int N, int nparts, int zslot, int cap, int f0i, int f1i,
                                                int k0, int k1) {
     // One iteration's operands: the taps of partitions q and q+1 for the thread's two bins, and the spectra of times
     // t0-q-1 and t0-q-2, which enter the window behind them.  They are loaded one iteration ahead (an iteration is ~570
     // instructions, more than a loaded HBM round trip) into the register set the other iteration does not use (the
-    // loop is unrolled by two by hand: no register moves), through running pointers (no index arithmetic).
+    // loop is unrolled by two by hand: no register moves), taps through running pointers, spectra through a running slot.
     struct Ops { float4 fa0, fb0, fa1, fb1, n0, n1; };
+    // `z`: the stream's circular time-ordered buffer (cap slots); `zslot`: the slot of the thread's first block t0
     const float4* pf0 = f + f0i;
     const float4* pf1 = f + f1i;
-    const float2* pz0 = z + ((long long)t0 - 1) * N + k0;
-    const float2* pz1 = z + ((long long)t0 - 1) * N + k1;
     const long long N2 = 2ll * N;
+    int sz = zslot - 1; if (sz < 0) sz += cap;   // slot of time t0-q-1, walking back two slots per iteration
     auto load = [&](Ops& o, int q) {
         if (q < nparts) { o.fa0 = pf0[0]; o.fb0 = pf1[0]; }
-        if (q + 1 < nparts) {
-            o.fa1 = pf0[N]; o.fb1 = pf1[N];
-            const float2 x = pz0[0], y = pz1[0];
-            o.n0 = make_float4(x.x, x.y, y.x, y.y);
-        }
-        if (q + 2 < nparts) {
-            const float2 x = pz0[-(long long)N], y = pz1[-(long long)N];
-            o.n1 = make_float4(x.x, x.y, y.x, y.y);
-        }
-        pf0 += N2; pf1 += N2; pz0 -= N2; pz1 -= N2;
+        if (q + 1 < nparts) { o.fa1 = pf0[N]; o.fb1 = pf1[N]; }
+        // the spectra loads are unconditional: a wrapped slot is always inside the stream's buffer, and a value that no
+        // partition needs is never used (a conditional load here compiles to a branch that pins the load behind it)
+        int s1 = sz - 1; if (s1 < 0) s1 += cap;
+        const float2* zp0 = z + (long long)sz * N;
+        const float2* zp1 = z + (long long)s1 * N;
+        const float2 x0 = zp0[k0], y0 = zp0[k1], x1 = zp1[k0], y1 = zp1[k1];
+        o.n0 = make_float4(x0.x, x0.y, y0.x, y0.y);
+        o.n1 = make_float4(x1.x, x1.y, y1.x, y1.y);
+        pf0 += N2; pf1 += N2;
+        sz = s1 - 1; if (sz < 0) sz += cap;
     };
     auto pair_step = [&](const Ops& o, int q) {
         const int rot = (TB - (q & (TB - 1))) & (TB - 1);   // slot of time t0+tb-q is (tb + rot) mod TB
@@ -183,7 +199,7 @@ template <int TB>
 __global__ void __launch_bounds__(128, 3) bin_conv_kernel(const float2* __restrict__ zlin, float2* __restrict__ wlin,
                                                        const float4* __restrict__ filt, const int* __restrict__ stream_hrir,
                                                        const int* __restrict__ set_parts, int N, int pmax, int K, int n_streams,
-                                                       long long zlin_stride) {
+                                                       long long zlin_stride, int zslot0, int cap) {
     static_assert((TB & (TB - 1)) == 0, "window slots are indexed modulo a power of two");
     extern __shared__ __align__(16) unsigned char smem[];
     float4* win = reinterpret_cast<float4*>(smem) + threadIdx.x;   // this thread's column: slot e at win[e * 128]
@@ -195,23 +211,35 @@ __global__ void __launch_bounds__(128, 3) bin_conv_kernel(const float2* __restri
     const int nparts = set_parts[set];
     const float4* f = filt + (size_t)set * pmax * N;
     const int f0i = (k0 & 1) * (N / 2) + (k0 >> 1), f1i = (k1 & 1) * (N / 2) + (k1 >> 1);   // even-bins-first table layout
-    const float2* z = zlin + (size_t)s * zlin_stride + (size_t)(pmax - 1) * N;   // z[tau * N + k]: time tau relative to block 0
+    const float2* z = zlin + (size_t)s * zlin_stride;   // circular: block t of this launch sits in slot (zslot0 + t) mod cap
+    int zs = zslot0 + t0; if (zs >= cap) zs -= cap;
     float2 a0[TB], a1[TB];
+    {
+        // the window's first TB spectra: every load unconditional (blocks past the launch's last re-read that one and are
+        // zeroed by a select) and issued before the first store, so that the TB round trips overlap
+        float2 v0[TB], v1[TB];
+        const int last = K - 1 - t0;
 #pragma unroll
-    for (int tb = 0; tb < TB; ++tb) {
-        a0[tb] = make_float2(0.f, 0.f); a1[tb] = make_float2(0.f, 0.f);
-        const bool live = t0 + tb < K;
-        const float2 v0 = live ? z[(size_t)(t0 + tb) * N + k0] : make_float2(0.f, 0.f);
-        const float2 v1 = live ? z[(size_t)(t0 + tb) * N + k1] : make_float2(0.f, 0.f);
-        win[tb * 128] = make_float4(v0.x, v0.y, v1.x, v1.y);
-        win[(tb + TB) * 128] = make_float4(v0.x, v0.y, v1.x, v1.y);
+        for (int tb = 0; tb < TB; ++tb) {
+            int sl = zs + (tb < last ? tb : last); if (sl >= cap) sl -= cap;
+            v0[tb] = z[(size_t)sl * N + k0];
+            v1[tb] = z[(size_t)sl * N + k1];
+        }
+#pragma unroll
+        for (int tb = 0; tb < TB; ++tb) {
+            a0[tb] = make_float2(0.f, 0.f); a1[tb] = make_float2(0.f, 0.f);
+            const bool live = tb <= last;
+            const float4 v = live ? make_float4(v0[tb].x, v0[tb].y, v1[tb].x, v1[tb].y) : make_float4(0.f, 0.f, 0.f, 0.f);
+            win[tb * 128] = v;
+            win[(tb + TB) * 128] = v;
+        }
     }
     // couple 0 (bins 0 and N/2, each its own mirror) lives in lane 0 of the first couple group's warps only
     if (blockIdx.x == 0) {
-        if (i == 0) bin_conv_steps<TB, true>(a0, a1, win, f, z, N, nparts, t0, f0i, f1i, k0, k1);
-        else bin_conv_steps<TB, false>(a0, a1, win, f, z, N, nparts, t0, f0i, f1i, k0, k1);
+        if (i == 0) bin_conv_steps<TB, true>(a0, a1, win, f, z, N, nparts, zs, cap, f0i, f1i, k0, k1);
+        else bin_conv_steps<TB, false>(a0, a1, win, f, z, N, nparts, zs, cap, f0i, f1i, k0, k1);
     } else {
-        bin_conv_steps<TB, false>(a0, a1, win, f, z, N, nparts, t0, f0i, f1i, k0, k1);
+        bin_conv_steps<TB, false>(a0, a1, win, f, z, N, nparts, zs, cap, f0i, f1i, k0, k1);
     }
     float2* w = wlin + ((size_t)s * K) * N;
 #pragma unroll
@@ -249,7 +277,7 @@ struct SpectrumStore {
 template <int N>
 __global__ void __launch_bounds__(SetupSmem<N>::TX) forward_kernel(const float* __restrict__ xf, long long xf_stride, int t0,
                                                                 const float* __restrict__ prev, float2* __restrict__ zlin,
-                                                                long long zlin_stride, int zlin_base, float2* __restrict__ fdl,
+                                                                long long zlin_stride, int zlin_base, int cap, float2* __restrict__ fdl,
                                                                 int pmax, int head, int ring_from, const int* __restrict__ stream_hrir,
                                                                 const int* __restrict__ set_parts, const float2* __restrict__ tw_g) {
     constexpr int T = SetupSmem<N>::TX, NP = SetupSmem<N>::NP, B = N / 2;
@@ -264,7 +292,8 @@ __global__ void __launch_bounds__(SetupSmem<N>::TX) forward_kernel(const float* 
     int slot = head + t;
     slot -= (slot / pmax) * pmax;
     float2* zr = (t >= ring_from && set_parts[stream_hrir[s]] > 1) ? fdl + ((size_t)s * pmax + slot) * N : nullptr;
-    float2* zl = zlin + (size_t)s * zlin_stride + (size_t)(zlin_base + t) * N;
+    int zs = zlin_base + t; if (zs >= cap) zs -= cap;   // circular time-ordered buffer (gather_history_kernel)
+    float2* zl = zlin + (size_t)s * zlin_stride + (size_t)zs * N;
     auto sync = [&]() { __syncthreads(); };
     fft_run<N, T>(threadIdx.x, tw_g, b0, b1, RowWindow{pl, pr, cl - B, cr - B, B}, SpectrumStore{zl, zr}, sync, [&]() {});
 }

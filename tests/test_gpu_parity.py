@@ -628,6 +628,39 @@ def test_time_batched_pipeline_variants(case, monkeypatch):
     assert np.array_equal(outs["0"], outs["1"])
 
 
+def test_time_batched_history_stays_in_the_circular_buffer():
+    """Consecutive time-batched calls keep their convolution history in the circular time-ordered buffer (no copy
+    between calls; the buffer wraps several times here); the delay-line ring is rebuilt from it only when something needs
+    it: a state export, a block-by-block call.  Five time-batched calls, export, import into a fresh engine, four blocks
+    block by block there, and two more on the first engine: all against the oracle."""
+    block, taps, n_streams = 128, 1100, 4
+    calls = [24, 16, 40, 8, 24]
+    n_blocks = sum(calls) + 4
+    h = S.synthetic_hrir_set(taps, taps / 5.0, seed=27)
+    x = S.stream_inputs(n_streams, block * n_blocks, base_seed=1270)
+    coeffs = preset_coeffs(S.EQ_PRESET_TYPICAL)
+    ref = oracle_render(x, block, h, coeffs, [1] * 10, 0.7)
+
+    def engine():
+        e = ohs.Engine(n_streams, block, taps)
+        e.set_hrir_set(h); e.eq_set_preset(S.EQ_PRESET_TYPICAL); e.set_eq_enable(True); e.set_gain(0.7)
+        return e
+
+    e = engine()
+    e.prepare(40 * block)            # scratch for the largest call: 8 history slots + 40 = 48 slots, 112 blocks go through
+    parts, at = [], 0
+    for k in calls:
+        parts.append(e.process(x[:, :, at * block:(at + k) * block])); at += k
+    blob = e.state_export()
+    f = engine()
+    f.state_import(blob)
+    tail_f = f.process(x[:, :, at * block:])                       # 4 blocks: block by block on the importing engine
+    tail_e = np.concatenate([e.process(x[:, :, at * block:(at + 2) * block]), e.process(x[:, :, (at + 2) * block:])], axis=2)
+    y = np.concatenate(parts + [tail_e], axis=2)
+    assert float(np.max(np.abs(y - ref))) <= TOL
+    assert np.array_equal(tail_f, tail_e)
+
+
 def test_time_batched_mixed_hrir_sets(monkeypatch):
     """Two HRIR sets on one engine, a long one (10 partitions) and a single-partition one, streams bound alternately:
     the time-batched route renders both kinds (a single-partition stream has no delay line of its own)."""
