@@ -379,9 +379,9 @@ def run_stream_config(ctx: Ctx, cfg_id: int, k_blocks: int, reps: int, also_bloc
         out["roofline_pipeline"] = {"bound": "hbm", "achieved": own / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": own / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_call": int(own),
                                     "formula": "(16*B + 8*S) per stream-block, S = 8*(B+1)",
-                                    "measured_dram_bytes_per_stream_block": 131800,
+                                    "measured_dram_bytes_per_stream_block": 99900,
                                     "measured_note": "ncu launch list of a serialised 64-block call (profiles/r02_ncu_launches_config5_time_batched_k64.csv): "
-                                                     "2.16 GB read + written per 64 blocks of 256 streams"}
+                                                     "1.64 GB read + written per 64 blocks of 256 streams"}
     # the same engine with fewer blocks per call (the EQ pre-pass of a call's first chunk and the transforms of its last are
     # not overlapped, so short calls pay more per block)
     for kb in also_blocks:
