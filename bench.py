@@ -395,6 +395,84 @@ def run_stream_config(ctx: Ctx, cfg_id: int, k_blocks: int, reps: int, also_bloc
     return out
 
 
+def run_single_stream_config(ctx: Ctx, reps: int):
+    """BASELINE config 1 (the reference's own CPU-runnable case): ONE stereo stream, 48 kHz, 10 s of pink noise, the
+    bundled CIPIC HRIRs (speakers at +-30 degrees: measurements 308 and 908 of tests/golden/cipic003_hrir.npz, 200 taps),
+    10-band PEQ, block 512.  One stream cannot fill a GPU: what is reported is latency — the per-block API (one call per
+    512-frame host buffer, the plugin's calling pattern) against the 10.67 ms such a buffer lasts — and the whole 10 s in
+    one call; parity of the full render against the oracle.  Rank 0 only (the config does not shard)."""
+    torch, pkg = ctx.torch, ctx.pkg
+    S = pkg.signals
+    fix = os.path.join(ROOT, "tests", "golden", "cipic003_hrir.npz")
+    if ctx.rank != 0 or not os.path.exists(fix):
+        ctx.barrier()
+        return None
+    from oracle import oracle as O
+
+    block, fs = 512, 48000.0
+    ir = np.load(fix)["ir"]
+    irs = [ir[308, 0], ir[308, 1], ir[908, 0], ir[908, 1]]
+    n_blocks = 938                      # 10 s = 480 000 frames, zero-padded to whole blocks
+    n = n_blocks * block
+    x = np.zeros((1, 2, n), np.float32)
+    x[0, 0, :480000] = S.pink_noise(480000, 1)
+    x[0, 1, :480000] = S.pink_noise(480000, 2)
+    coeffs = np.stack([pkg.eq_design(t, fs, fc, q, g) for (t, fc, q, g) in S.EQ_PRESET_TYPICAL])
+    eng = pkg.Engine(1, block, 200, device=ctx.local, sample_rate=fs)
+    eng.set_hrir_set(irs)
+    for b in range(10):
+        eng.eq_set_band(b, coeffs[b], True)
+    eng.set_eq_enable(True); eng.set_gain(GAIN)
+    d_in = torch.from_numpy(x).to(ctx.dev)
+    d_out = torch.empty_like(d_in)
+    stream = torch.cuda.ExternalStream(eng.cuda_stream(), device=ctx.dev)
+    torch.cuda.synchronize()
+    eng.process_device(d_in.data_ptr(), d_out.data_ptr(), n)       # first call from zero state: the parity run
+    eng.sync()
+    ref, _ = O.render_batch(x, block, irs, coeffs, [1] * 10, True, GAIN, n_threads=1)
+    err = float(np.max(np.abs(d_out.cpu().numpy() - ref)))
+
+    def whole():
+        eng.process_device(d_in.data_ptr(), d_out.data_ptr(), n)
+
+    def per_block(k=64):
+        for t in range(k):
+            eng.process_device(d_in.data_ptr() + 4 * t * block, d_out.data_ptr() + 4 * t * block, block, row_stride=n)
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, r):
+        fn()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(r):
+                fn()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / r
+
+    ms_whole = timed(whole, reps)
+    ms_block = timed(per_block, reps) / 64
+    # one call per host buffer WITH the host waiting for the result (what a real-time caller sees)
+    t0 = time.perf_counter()
+    for t in range(64):
+        eng.process_device(d_in.data_ptr() + 4 * t * block, d_out.data_ptr() + 4 * t * block, block, row_stride=n)
+        eng.sync()
+    ms_sync = (time.perf_counter() - t0) * 1e3 / 64
+    buffer_ms = block / fs * 1e3
+    out = {"workload": S.CONFIGS[1]["name"], "block": block, "taps": 200, "sample_rate": fs, "seconds": 10.0,
+           "whole_render_ms": ms_whole, "value": (n / fs) / (ms_whole * 1e-3), "unit": UNIT,
+           "per_block_api": {"us_per_block_device": ms_block * 1e3, "us_per_block_with_host_sync": ms_sync * 1e3,
+                             "host_buffer_ms": buffer_ms, "real_time_factor": buffer_ms / ms_sync},
+           "note": "one stream = one CTA: latency, not roofline (SURVEY.md 8d); the whole render is bound by the sequential biquad chain "
+                   "(480 000 steps)",
+           "parity_max_abs": err, "parity_bar": 1e-5, "parity_extent": "all 938 blocks against the oracle"}
+    del eng, d_in, d_out
+    ctx.barrier()
+    return out
+
+
 def run_object_config(ctx: Ctx, reps: int):
     """BASELINE config 4: 512 mono sources per GPU, each with its own direction from the bundled CIPIC set, 10 s at
     48 kHz, binaurally mixed to one stereo bus; ncclReduce of the per-GPU buses and the bus EQ + gain on rank 0 are
@@ -550,6 +628,9 @@ def run_gpu(args, pkg):
     if not args.no_configs:
         del d_in, d_out
         torch.cuda.empty_cache()
+        c1 = run_single_stream_config(ctx, reps=3)
+        if c1 is not None:
+            configs["cfg1"] = c1
         configs["cfg3"] = run_stream_config(ctx, 3, 128, reps=5)
         configs["cfg5"] = run_stream_config(ctx, 5, 512, reps=3, also_blocks=(64, 256))
         configs["cfg4"] = run_object_config(ctx, reps=3)
