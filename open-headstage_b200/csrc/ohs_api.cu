@@ -408,7 +408,7 @@ template <int N> int launch_inverse(ohs_engine* h, const float2* d_w, float* d_o
 }
 
 // forward transforms of blocks [t0, t0 + k) of a sub-launch from the filtered rows xf (block 0's history: d_prev)
-template <int N> int launch_forward(ohs_engine* h, const float* xf, long long xf_stride, int t0, int k, long long zstride, int zbase, int ring_from) {
+template <int N> int launch_forward(ohs_engine* h, const float* xf, long long xf_stride, int t0, int k, long long zstride, int zbase) {
     // zbase: the time-ordered buffer's slot of the sub-launch's block 0
     constexpr size_t smem = sizeof(float2) * 2 * padded_len(N);
     static AttrOnce once;
@@ -418,8 +418,7 @@ template <int N> int launch_forward(ohs_engine* h, const float* xf, long long xf
         once.mark(dev);
     }
     forward_kernel<N><<<dim3(k, h->cfg.n_streams), SetupSmem<N>::TX, smem, h->stream>>>(
-        xf, xf_stride, t0, reinterpret_cast<const float*>(h->d_prev), h->d_zlin, zstride, zbase, h->zl_cap, h->d_fdl, h->pmax, h->head, ring_from,
-        h->d_stream_hrir, h->d_set_parts, h->d_tw);
+        xf, xf_stride, t0, reinterpret_cast<const float*>(h->d_prev), h->d_zlin, zstride, zbase, h->zl_cap, h->d_tw);
     OHS_CUDA(cudaGetLastError());
     h->launches++;
     return OHS_OK;
@@ -646,11 +645,11 @@ int process_time_batched(ohs_engine* h, RenderParams p, const float* d_in, float
             if (overlap) OHS_CUDA(cudaStreamWaitEvent(h->stream, done_ev[j][ci], 0));
             int rc;
             switch (h->N) {
-                case 128: rc = launch_forward<128>(h, xf, xs, c0, ck, zstride, zb, 1 << 30); break;
-                case 256: rc = launch_forward<256>(h, xf, xs, c0, ck, zstride, zb, 1 << 30); break;
-                case 512: rc = launch_forward<512>(h, xf, xs, c0, ck, zstride, zb, 1 << 30); break;
-                case 1024: rc = launch_forward<1024>(h, xf, xs, c0, ck, zstride, zb, 1 << 30); break;
-                case 2048: rc = launch_forward<2048>(h, xf, xs, c0, ck, zstride, zb, 1 << 30); break;
+                case 128: rc = launch_forward<128>(h, xf, xs, c0, ck, zstride, zb); break;
+                case 256: rc = launch_forward<256>(h, xf, xs, c0, ck, zstride, zb); break;
+                case 512: rc = launch_forward<512>(h, xf, xs, c0, ck, zstride, zb); break;
+                case 1024: rc = launch_forward<1024>(h, xf, xs, c0, ck, zstride, zb); break;
+                case 2048: rc = launch_forward<2048>(h, xf, xs, c0, ck, zstride, zb); break;
                 default: rc = fail(OHS_ERR_INVALID, "unsupported transform size %d", h->N);
             }
             if (rc) return rc;

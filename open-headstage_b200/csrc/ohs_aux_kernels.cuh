@@ -258,28 +258,25 @@ struct RowWindow {
     }
 };
 
-// last-pass store of the forward transform: the packed spectrum goes to the time-ordered buffer and (streams that keep
-// a delay line) to the ring slot, straight from registers
+// last-pass store of the forward transform: the packed spectrum goes straight from registers to its slot of the
+// time-ordered buffer
 struct SpectrumStore {
-    float2* zl; float2* zr;   // zr may be null
-    __device__ __forceinline__ void st(int i, float2 v) const { zl[i] = v; if (zr) zr[i] = v; }
+    float2* zl;
+    __device__ __forceinline__ void st(int i, float2 v) const { zl[i] = v; }
     __device__ __forceinline__ void st2(int i, float2 a, float2 b) const {
-        const float4 v = make_float4(a.x, a.y, b.x, b.y);
-        *reinterpret_cast<float4*>(zl + i) = v;
-        if (zr) *reinterpret_cast<float4*>(zr + i) = v;
+        *reinterpret_cast<float4*>(zl + i) = make_float4(a.x, a.y, b.x, b.y);
     }
 };
 
 // one CTA per (block, stream): forward transform of block t0 + blockIdx.x of the filtered rows `xf` (block 0's history is
-// the engine's overlap-save block `prev`), same plan and rounding as the render kernel's forward transform.  Only blocks
-// t >= ring_from (the sub-launch's last pmax blocks) go to the delay-line ring: the blocks of a launch run concurrently,
-// and two blocks pmax apart share a ring slot
+// the engine's overlap-save block `prev`), same plan and rounding as the render kernel's forward transform, into slot
+// (zlin_base + t) mod cap of the circular time-ordered buffer.  (The delay-line ring is not written here: it is rebuilt
+// from the buffer when something needs it, scatter_history_kernel.)
 template <int N>
 __global__ void __launch_bounds__(SetupSmem<N>::TX) forward_kernel(const float* __restrict__ xf, long long xf_stride, int t0,
-                                                                const float* __restrict__ prev, float2* __restrict__ zlin,
-                                                                long long zlin_stride, int zlin_base, int cap, float2* __restrict__ fdl,
-                                                                int pmax, int head, int ring_from, const int* __restrict__ stream_hrir,
-                                                                const int* __restrict__ set_parts, const float2* __restrict__ tw_g) {
+                                                                 const float* __restrict__ prev, float2* __restrict__ zlin,
+                                                                 long long zlin_stride, int zlin_base, int cap,
+                                                                 const float2* __restrict__ tw_g) {
     constexpr int T = SetupSmem<N>::TX, NP = SetupSmem<N>::NP, B = N / 2;
     extern __shared__ __align__(16) unsigned char smem[];
     float2* b0 = reinterpret_cast<float2*>(smem);
@@ -289,13 +286,10 @@ __global__ void __launch_bounds__(SetupSmem<N>::TX) forward_kernel(const float* 
     const float* cr = cl + xf_stride;
     const float* pl = t ? cl - B : prev + (size_t)s * 2 * B;
     const float* pr = t ? cr - B : pl + B;
-    int slot = head + t;
-    slot -= (slot / pmax) * pmax;
-    float2* zr = (t >= ring_from && set_parts[stream_hrir[s]] > 1) ? fdl + ((size_t)s * pmax + slot) * N : nullptr;
-    int zs = zlin_base + t; if (zs >= cap) zs -= cap;   // circular time-ordered buffer (gather_history_kernel)
+    int zs = zlin_base + t; if (zs >= cap) zs -= cap;
     float2* zl = zlin + (size_t)s * zlin_stride + (size_t)zs * N;
     auto sync = [&]() { __syncthreads(); };
-    fft_run<N, T>(threadIdx.x, tw_g, b0, b1, RowWindow{pl, pr, cl - B, cr - B, B}, SpectrumStore{zl, zr}, sync, [&]() {});
+    fft_run<N, T>(threadIdx.x, tw_g, b0, b1, RowWindow{pl, pr, cl - B, cr - B, B}, SpectrumStore{zl}, sync, [&]() {});
 }
 
 // first-pass loader of the inverse transform from global memory, with the swap of swap o FFT o swap
